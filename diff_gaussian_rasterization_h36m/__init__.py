@@ -1,0 +1,11 @@
+"""Drop-in for the reference's ``diff_gaussian_rasterization_h36m`` package
+(submodules/diff-gaussian-rasterization-h36m; NUM_CHANNELS = 17, cuda_rasterizer/config.h:15),
+backed by skelsplat_b200's sm_100a library.  Imported by gaussian_renderer/__init__.py:15-22."""
+from skelsplat_b200.rasterizer import GaussianRasterizationSettings, rasterize_gaussians  # noqa: F401
+from skelsplat_b200.rasterizer import GaussianRasterizer as _Base
+
+NUM_CHANNELS = 17
+
+
+class GaussianRasterizer(_Base):
+    NUM_CHANNELS = NUM_CHANNELS

@@ -1,0 +1,93 @@
+"""Hyper-parameters of the reference's shipped training configs, as plain dataclasses.
+
+Values are those of configs/{h36m,h36m-occ,panoptic,occlusion-person}.yaml in the
+reference (file:line cited per field).  hydra/omegaconf are config plumbing and out of
+scope; only the numbers that reach the hot path live here.
+"""
+from dataclasses import dataclass, field, replace
+from typing import Tuple
+
+
+@dataclass(frozen=True)
+class SceneConfig:
+    name: str                     # dataset.data_root basename == Scene.scene_type (scene/__init__.py:37)
+    n_joints: int                 # scene/__init__.py:50-58
+    image_sizes: Tuple[Tuple[int, int], ...]   # (W, H) per view; scene/dataset_readers.py:68-80,106-124
+    rendering: str                # pipeline.rendering, configs/*.yaml:45
+    nviews: int = 4               # dataset.nviews, configs/*.yaml:16
+    # training (configs/*.yaml:18-27)
+    accumulation_steps: int = 4
+    loss_function: str = "l2_gaussian"
+    lambda_loss_function: float = 0.05
+    consistency_loss: str = "3D_length_consistency"
+    lambda_consistency: float = 1e-5
+    # model (configs/*.yaml:33-42)
+    scaling: float = 3.0
+    scaling_modifier: float = 1.0
+    opacity_on: bool = True
+    # optimisation (configs/*.yaml:51-75)
+    iterations: int = 500
+    position_lr_init: float = 0.0005
+    position_lr_final: float = 0.000005
+    position_lr_delay_mult: float = 0.0
+    position_lr_max_steps: int = 4000
+    feature_lr: float = 0.0
+    opacity_lr: float = 0.0
+    scaling_lr: float = 0.005
+    rotation_lr: float = 0.001
+    # limb pairs of limb_3d_consistency_loss (utils/loss_utils.py:226-250): (l_arm, r_arm, l_leg, r_leg)
+    limb_pairs: Tuple[Tuple[int, int], ...] = ((12, 13), (15, 16), (5, 6), (2, 3))
+    # joints whose initial raw scale is multiplied by scaling_modifier
+    # (scene/gaussian_model.py:170-178; exact scene_type match, so "h36m-occ" gets none)
+    modifier_joints: Tuple[int, ...] = ()
+    # synthetic-data knobs
+    cam_ring_radius_mm: Tuple[float, float] = (4500.0, 5500.0)
+    focal_range: Tuple[float, float] = (1140.0, 1150.0)
+    det_noise_px: float = 3.0
+    occluded: bool = False
+
+    @property
+    def antialiasing(self):
+        return False               # pipeline.antialiasing, configs/*.yaml:49
+
+
+H36M = SceneConfig(
+    name="h36m", n_joints=17,
+    image_sizes=((1002, 1000), (1000, 1000), (1000, 1000), (1002, 1000)),
+    rendering="diff-gaussian-rasterization-h36m",
+    modifier_joints=(3, 6, 12, 13, 15, 16),
+)
+
+# data_root "data/h36m-occ": scaling_modifier 1.25 in the yaml is a no-op because
+# scene_type == "h36m-occ" matches no branch of create_from_pcd.
+H36M_OCC = replace(H36M, name="h36m-occ", scaling_modifier=1.25, modifier_joints=(), occluded=True)
+
+PANOPTIC = SceneConfig(
+    name="panoptic", n_joints=19,
+    image_sizes=((1920, 1080),) * 4,
+    rendering="diff-gaussian-rasterization-panoptic",
+    position_lr_init=0.005, opacity_lr=0.005,
+    limb_pairs=((4, 5), (10, 11), (7, 8), (13, 14)),
+    modifier_joints=(8, 14, 4, 5, 10, 11),
+    cam_ring_radius_mm=(2500.0, 3500.0), focal_range=(1390.0, 1410.0),
+)
+
+OCCLUSION_PERSON = SceneConfig(
+    name="occlusion-person", n_joints=15,
+    image_sizes=((1280, 720),) * 4,
+    rendering="diff-gaussian-rasterization-op",
+    scaling_modifier=1.25, position_lr_init=0.005, rotation_lr=0.0,
+    limb_pairs=((10, 11), (13, 14), (5, 6), (2, 3)),
+    modifier_joints=(3, 6, 10, 11, 13, 14),
+    focal_range=(1050.0, 1150.0),
+)
+
+# BASELINE.json config 5: the 8-view throughput sweep (the yaml ships nviews: 4).
+OCCLUSION_PERSON_8V = replace(OCCLUSION_PERSON, nviews=8, image_sizes=((1280, 720),) * 8)
+
+CONFIGS = {c.name: c for c in (H36M, H36M_OCC, PANOPTIC, OCCLUSION_PERSON)}
+CONFIGS["occlusion-person-8v"] = OCCLUSION_PERSON_8V
+
+
+def get_config(name: str) -> SceneConfig:
+    return CONFIGS[name]

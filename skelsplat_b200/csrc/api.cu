@@ -1,0 +1,26 @@
+// Library-level entry points: version, error strings.
+#include <cstring>
+#include "api_internal.h"
+
+static thread_local char g_last_cuda_error[256] = "";
+
+int ssb_set_cuda_error(cudaError_t e) {
+    if (e == cudaSuccess) return SSB_OK;
+    std::strncpy(g_last_cuda_error, cudaGetErrorString(e), sizeof(g_last_cuda_error) - 1);
+    return SSB_ERR_CUDA;
+}
+
+extern "C" {
+int ssb_version(void) { return 100; }
+const char* ssb_last_cuda_error(void) { return g_last_cuda_error; }
+const char* ssb_error_string(int code) {
+    switch (code) {
+        case SSB_OK: return "ok";
+        case SSB_ERR_INVALID: return "invalid argument";
+        case SSB_ERR_CAPACITY: return "capacity exceeded (P > 1024, r_capacity out of range, or buffer too small)";
+        case SSB_ERR_CUDA: return "CUDA runtime error";
+        case SSB_ERR_UNSUPPORTED: return "unsupported configuration (channel count not instantiated)";
+        default: return "unknown error";
+    }
+}
+}

@@ -1,0 +1,567 @@
+// Fused per-frame optimiser: the whole SkelSplat iteration loop in one persistent kernel, sm_100a.
+//
+// Replaces, per frame, 500 x (render_* + l2_loss_gaussian + limb consistency + autograd.grad +
+// gradient bookkeeping) + 125 x torch.optim.Adam.step  (train.py:130-233, ~50 launches and 5 host
+// syncs per iteration in the reference) by ONE kernel launch for any number of frames.
+//
+// Design (DESIGN.md section "optimiser"):
+//   * one CTA owns one frame for all iterations; parameters, Adam moments and the per-view gradient
+//     slots live in shared memory; nothing but the GT heatmap ROIs is read from HBM/L2 in the loop;
+//   * parameters only change every `accumulation_steps` iterations, so the iterations of one step
+//     group are independent: they are processed concurrently as SLOTS "slots" (sequential depth 125
+//     instead of 500), each with its own binning state;
+//   * binning = (tile|depth) keys sorted by an in-shared-memory bitonic network (same keys and
+//     order as the dense rasteriser => same tile lists as the reference);
+//   * compositing is never materialised: each warp owns an active tile, walks its 8 row pairs,
+//     evaluates forward + loss + backward per pixel with the GT read from the ROI patch, keeps the
+//     per-(tile,Gaussian) gradient sums in registers and reduces them once per tile with a
+//     transposing shuffle butterfly (9 shuffles for 8 values) - no atomics, deterministic;
+//   * the one-hot feature structure (Gaussian j renders only into channel j; frozen in the
+//     reference: scene/gaussian_model.py:159-166,186) collapses the reference's per-channel
+//     backward recurrence into one scalar recurrence per pixel;
+//   * Adam (torch.optim.Adam semantics, eps=1e-15) runs in-kernel with host-computed fp64 step sizes.
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+#include "api_internal.h"
+
+namespace ssb {
+
+constexpr int OPT_THREADS = 256;
+constexpr int OPT_WARPS = OPT_THREADS / 32;
+constexpr int MAXJ = 20;
+constexpr int MAXV = 8;
+constexpr int MAX_SLOTS = 4;
+constexpr int MAX_STEPS = 256;
+constexpr int FAST = 4;            // tile-list entries whose gradient sums are held in registers at once
+constexpr int NPART = 6;           // dmean2D.x, dmean2D.y, dconic.x, dconic.y, dconic.w, dopacity
+
+struct StepTable {                 // host-computed in fp64, rounded to fp32 like torch's scalar->tensor ops
+    float neg_step_xyz[MAX_STEPS];
+    float neg_step_scaling[MAX_STEPS];
+    float neg_step_rotation[MAX_STEPS];
+    float neg_step_opacity[MAX_STEPS];
+    float bc2_sqrt[MAX_STEPS];
+};
+
+struct OptParams {
+    ssb_opt_config cfg;
+    ssb_cameras cams;
+    int n_frames, n_steps;
+    float* xyz; float* scaling_raw; float* rotation_raw; float* opacity_raw;
+    const int* roi_rect; const int64_t* roi_offset; const float* roi_data;
+    float* final_loss; int* status;
+};
+
+// Reduce V (power of two) values across the warp with V-1+log2(32/V) shuffles.  On return every lane
+// holds the full sum of value index  j(lane) = sum over halving steps of (lane & off ? n/2 : 0).
+template <int V>
+__device__ __forceinline__ float warp_multi_reduce(float (&v)[V], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = V; n > 1; n >>= 1) {
+        const int half = n >> 1;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+        }
+        off >>= 1;
+    }
+    float x = v[0];
+    for (; off > 0; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
+    return x;
+}
+
+// Per-slot splat state (structure of arrays in shared memory).
+struct SlotSplats {
+    float px[MAXJ], py[MAXJ], conx[MAXJ], cony[MAXJ], conz[MAXJ], opac[MAXJ];
+    uint32_t depth_bits[MAXJ];
+    uint16_t rx0[MAXJ], ry0[MAXJ], rx1[MAXJ], ry1[MAXJ];
+    uint16_t tiles[MAXJ], offs[MAXJ];      // tiles touched, inclusive scan
+};
+
+template <int SLOTS>
+__global__ void __launch_bounds__(OPT_THREADS, 2)
+optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ StepTable tab)
+{
+    const int J = p.cfg.J, V = p.cfg.V, RCAP = p.cfg.r_capacity;
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---------------- shared memory ----------------
+    __shared__ float s_xyz[MAXJ * 3], s_scal[MAXJ * 3], s_rot[MAXJ * 4], s_opa[MAXJ];       // raw parameters
+    __shared__ float s_m[MAXJ * 11], s_v[MAXJ * 11];                                          // Adam moments
+    __shared__ float s_grad[MAXJ * 11];                                                       // grads of the step
+    __shared__ float s_accg[MAXV][MAXJ * 3];                                                  // accumulated_grads[V,J,3]
+    __shared__ float s_act_scale[MAXJ * 3], s_act_q[MAXJ * 4], s_act_qn[MAXJ], s_act_op[MAXJ], s_cov3d[MAXJ * 6];
+    __shared__ float s_view[MAXV][16], s_proj[MAXV][16];
+    __shared__ int s_W[MAXV], s_H[MAXV];
+    __shared__ float s_tfx[MAXV], s_tfy[MAXV], s_fx[MAXV], s_fy[MAXV];
+    __shared__ int s_roi[MAXV][MAXJ][4];
+    __shared__ long long s_roi_off[MAXV][MAXJ];
+    __shared__ int s_ngt[MAXV];            // sum_j #{gt > 0}
+    __shared__ float s_sgt2[MAXV];         // sum_j sum gt^2
+    __shared__ SlotSplats s_sp[SLOTS];
+    __shared__ int s_R[SLOTS], s_nact[SLOTS], s_cnt[SLOTS];
+    __shared__ float s_lsum[SLOTS][OPT_WARPS];
+    __shared__ int s_status;
+    extern __shared__ __align__(16) unsigned char dsm[];
+    // dynamic: per slot keys u64[RCAP] | sortvals u32[RCAP] | list u16[RCAP] | inv_pos u16[RCAP] | tile u16[RCAP] | start u16[RCAP] | partial f32[RCAP*NPART]
+    uint64_t* d_keys = reinterpret_cast<uint64_t*>(dsm);
+    uint32_t* d_vals = reinterpret_cast<uint32_t*>(d_keys + (size_t)SLOTS * RCAP);
+    float* d_part = reinterpret_cast<float*>(d_vals + (size_t)SLOTS * RCAP);
+    uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)SLOTS * RCAP * NPART);
+    uint16_t* d_inv = d_list + (size_t)SLOTS * RCAP;
+    uint16_t* d_tile = d_inv + (size_t)SLOTS * RCAP;
+    uint16_t* d_start = d_tile + (size_t)SLOTS * RCAP;
+
+    // ---------------- load the frame ----------------
+    for (int i = tid; i < J * 3; i += OPT_THREADS) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
+    for (int i = tid; i < J * 4; i += OPT_THREADS) s_rot[i] = p.rotation_raw[(size_t)frame * J * 4 + i];
+    for (int i = tid; i < J; i += OPT_THREADS) s_opa[i] = p.opacity_raw[(size_t)frame * J + i];
+    for (int i = tid; i < J * 11; i += OPT_THREADS) { s_m[i] = 0.f; s_v[i] = 0.f; s_grad[i] = 0.f; }
+    for (int i = tid; i < MAXV * MAXJ * 3; i += OPT_THREADS) (&s_accg[0][0])[i] = 0.f;
+    for (int i = tid; i < V * 16; i += OPT_THREADS) { s_view[i / 16][i % 16] = p.cams.viewmatrix[i]; s_proj[i / 16][i % 16] = p.cams.projmatrix[i]; }
+    if (tid < V) {
+        const int W = p.cams.dims ? p.cams.dims[2 * tid] : p.cams.W0, H = p.cams.dims ? p.cams.dims[2 * tid + 1] : p.cams.H0;
+        const float tfx = p.cams.tanfov ? p.cams.tanfov[2 * tid] : p.cams.tanfovx0, tfy = p.cams.tanfov ? p.cams.tanfov[2 * tid + 1] : p.cams.tanfovy0;
+        s_W[tid] = W; s_H[tid] = H; s_tfx[tid] = tfx; s_tfy[tid] = tfy;
+        s_fy[tid] = __fdiv_rn((float)H, __fmul_rn(2.0f, tfy));
+        s_fx[tid] = __fdiv_rn((float)W, __fmul_rn(2.0f, tfx));
+        s_ngt[tid] = 0; s_sgt2[tid] = 0.f;
+    }
+    for (int i = tid; i < V * J; i += OPT_THREADS) {
+        const int v = i / J, j = i % J;
+        const size_t o = ((size_t)frame * V + v) * J + j;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s_roi[v][j][k] = p.roi_rect[4 * o + k];
+        s_roi_off[v][j] = p.roi_offset[o];
+    }
+    if (tid == 0) s_status = 0;
+    __syncthreads();
+    // GT statistics of the loss mask: N_gt = #{gt>0}, S = sum gt^2 (per view; fixed-order per-warp sums)
+    for (int v = 0; v < V; v++) {
+        int cnt = 0; float sq = 0.f;
+        for (int j = 0; j < J; j++) {
+            const int n = s_roi[v][j][2] * s_roi[v][j][3];
+            const float* d = p.roi_data + s_roi_off[v][j];
+            for (int i = tid; i < n; i += OPT_THREADS) { const float g = __ldg(d + i); if (g > 0.f) { cnt++; sq = fmaf(g, g, sq); } }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); }
+        if (lane == 0) { s_lsum[0][warp] = sq; atomicAdd(&s_ngt[v], cnt); }
+        __syncthreads();
+        if (tid == 0) { float a = 0.f; for (int w = 0; w < OPT_WARPS; w++) a += s_lsum[0][w]; s_sgt2[v] = a; }
+        __syncthreads();
+    }
+
+    const int acc = p.cfg.accumulation_steps;     // == SLOTS (host guarantees)
+    float last_loss = 0.f;
+
+    for (int step = 0; step < p.n_steps; step++) {
+        // ============ phase A: activations + projection of every (slot, joint) ============
+        if (tid < J) {
+            const int j = tid;
+            // GaussianModel getters (scene/gaussian_model.py:102-143): exp / normalize / sigmoid
+            const float sx = expf(s_scal[3 * j]), sy = expf(s_scal[3 * j + 1]), sz = expf(s_scal[3 * j + 2]);
+            const float q0 = s_rot[4 * j], q1 = s_rot[4 * j + 1], q2 = s_rot[4 * j + 2], q3 = s_rot[4 * j + 3];
+            const float qn = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);   // F.normalize eps
+            const float r = q0 / qn, x = q1 / qn, y = q2 / qn, z = q3 / qn;
+            s_act_scale[3 * j] = sx; s_act_scale[3 * j + 1] = sy; s_act_scale[3 * j + 2] = sz;
+            s_act_q[4 * j] = r; s_act_q[4 * j + 1] = x; s_act_q[4 * j + 2] = y; s_act_q[4 * j + 3] = z;
+            s_act_qn[j] = qn;
+            s_act_op[j] = 1.0f / (1.0f + expf(-s_opa[j]));
+            float cov[6];
+            cov3d_from_scale_rot(sx, sy, sz, 1.0f, r, x, y, z, cov);
+#pragma unroll
+            for (int k = 0; k < 6; k++) s_cov3d[6 * j + k] = cov[k];
+        }
+        if (tid < SLOTS) { s_cnt[tid] = 0; }
+        if (tid < SLOTS * OPT_WARPS) (&s_lsum[0][0])[tid] = 0.f;
+        __syncthreads();
+        if (tid < SLOTS * J) {
+            const int k = tid / J, j = tid % J;
+            const int v = (step * acc + k) % V;
+            const Splat s = project_gaussian(s_xyz[3 * j], s_xyz[3 * j + 1], s_xyz[3 * j + 2], &s_cov3d[6 * j], s_act_op[j],
+                                             s_view[v], s_proj[v], s_W[v], s_H[v], s_tfx[v], s_tfy[v], s_fx[v], s_fy[v],
+                                             p.cfg.antialiasing != 0);
+            SlotSplats& sp = s_sp[k];
+            sp.px[j] = s.px; sp.py[j] = s.py; sp.conx[j] = s.conx; sp.cony[j] = s.cony; sp.conz[j] = s.conz; sp.opac[j] = s.opac;
+            sp.depth_bits[j] = __float_as_uint(s.depth);
+            sp.rx0[j] = (uint16_t)s.rect.x0; sp.ry0[j] = (uint16_t)s.rect.y0; sp.rx1[j] = (uint16_t)s.rect.x1; sp.ry1[j] = (uint16_t)s.rect.y1;
+            sp.tiles[j] = (uint16_t)min(s.tiles, 65535u);
+        }
+        __syncthreads();
+        // ============ phase B: binning (scan, keys, sort, tile runs) per slot ============
+        if (tid < SLOTS) {
+            SlotSplats& sp = s_sp[tid];
+            uint32_t a = 0;
+            for (int j = 0; j < J; j++) { a += sp.tiles[j]; sp.offs[j] = (uint16_t)min(a, 65535u); }
+            if (a > (uint32_t)RCAP) { s_status |= (int)SSB_STATUS_R_OVERFLOW; a = RCAP; }
+            s_R[tid] = (int)a;
+        }
+        __syncthreads();
+        int nsort = 32;
+        {
+            int Rmax = 0;
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) Rmax = max(Rmax, s_R[k]);
+            while (nsort < Rmax) nsort <<= 1;       // RCAP is a power of two >= Rmax
+        }
+        for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
+            const int k = i / nsort, e = i - k * nsort;
+            d_keys[(size_t)k * RCAP + e] = ~0ull; d_vals[(size_t)k * RCAP + e] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        if (tid < SLOTS * J) {
+            const int k = tid / J, j = tid % J;
+            const SlotSplats& sp = s_sp[k];
+            if (sp.tiles[j] > 0) {
+                const int v = (step * acc + k) % V;
+                const uint32_t gx = (uint32_t)((s_W[v] + TILE - 1) / TILE);
+                uint32_t off = (j == 0) ? 0u : sp.offs[j - 1];
+                for (uint32_t y = sp.ry0[j]; y < sp.ry1[j]; y++)
+                    for (uint32_t x = sp.rx0[j]; x < sp.rx1[j]; x++) {
+                        if (off < (uint32_t)s_R[k]) {
+                            d_keys[(size_t)k * RCAP + off] = ((uint64_t)(y * gx + x) << 32) | sp.depth_bits[j];
+                            d_vals[(size_t)k * RCAP + off] = (off << 10) | (uint32_t)j;
+                        }
+                        off++;
+                    }
+            }
+        }
+        __syncthreads();
+        // bitonic sort of all slots at once (independent sub-arrays of length nsort)
+        for (int kk = 2; kk <= nsort; kk <<= 1) {
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
+                    const int k = i / nsort, e = i - k * nsort;
+                    const int exj = e ^ jj;
+                    if (exj > e) {
+                        uint64_t* K = d_keys + (size_t)k * RCAP;
+                        uint32_t* Vv = d_vals + (size_t)k * RCAP;
+                        const uint64_t ka = K[e], kb = K[exj];
+                        const uint32_t va = Vv[e], vb = Vv[exj];
+                        const bool a_gt_b = (ka > kb) || (ka == kb && va > vb);
+                        if (a_gt_b == ((e & kk) == 0)) { K[e] = kb; K[exj] = ka; Vv[e] = vb; Vv[exj] = va; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
+            const int k = i / nsort, e = i - k * nsort;
+            if (e < s_R[k]) {
+                const uint32_t val = d_vals[(size_t)k * RCAP + e];
+                d_list[(size_t)k * RCAP + e] = (uint16_t)(val & 1023u);
+                d_inv[(size_t)k * RCAP + (val >> 10)] = (uint16_t)e;
+            }
+        }
+        if (warp < SLOTS) {      // warp k: ordered compaction of the tile runs of slot k
+            const int k = warp, R = s_R[k];
+            const uint64_t* K = d_keys + (size_t)k * RCAP;
+            int nact = 0;
+            for (int base = 0; base < R; base += 32) {
+                const int i = base + lane;
+                bool start = false; uint32_t tile = 0;
+                if (i < R) { tile = (uint32_t)(K[i] >> 32); start = (i == 0) || ((uint32_t)(K[i - 1] >> 32) != tile); }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, start);
+                if (start) {
+                    const int a = nact + __popc(m & ((1u << lane) - 1u));
+                    d_tile[(size_t)k * RCAP + a] = (uint16_t)tile;
+                    d_start[(size_t)k * RCAP + a] = (uint16_t)i;
+                }
+                nact += __popc(m);
+            }
+            if (lane == 0) s_nact[k] = nact;
+        }
+        __syncthreads();
+
+        // ============ phase C: tiles.  One warp per active tile, static round-robin ============
+        {
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) total += s_nact[k];
+            float lsum[SLOTS];
+            int lcnt[SLOTS];
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) { lsum[k] = 0.f; lcnt[k] = 0; }
+            for (int item = warp; item < total; item += OPT_WARPS) {
+                int k = 0, a = item;
+#pragma unroll
+                for (int kk = 0; kk < SLOTS - 1; kk++) { if (k == kk && a >= s_nact[kk]) { a -= s_nact[kk]; k = kk + 1; } }
+                const int v = (step * acc + k) % V;
+                const int W = s_W[v], H = s_H[v];
+                const int gx = (W + TILE - 1) / TILE;
+                const int tile = d_tile[(size_t)k * RCAP + a];
+                const int e0 = d_start[(size_t)k * RCAP + a];
+                const int e1 = (a + 1 < s_nact[k]) ? (int)d_start[(size_t)k * RCAP + a + 1] : s_R[k];
+                const int n = e1 - e0;
+                const SlotSplats& sp = s_sp[k];
+                const uint16_t* list = d_list + (size_t)k * RCAP + e0;
+                const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
+                const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+                float my_lsum = 0.f; int my_cnt = 0;
+                for (int c0 = 0; c0 < n; c0 += FAST) {
+                    float accv[FAST][NPART];
+#pragma unroll
+                    for (int u = 0; u < FAST; u++)
+#pragma unroll
+                        for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
+                    for (int pass = 0; pass < TILE / 2; pass++) {
+                        const int px = tx0 + (lane & 15), py = ty0 + 2 * pass + (lane >> 4);
+                        const bool inside = px < W && py < H;
+                        if (!inside) continue;          // no warp-collective operation inside the pass loop
+                        const float pxf = (float)px, pyf = (float)py;
+                        // forward replay: final transmittance and last contributor (forward.cu:330-386)
+                        float T = 1.0f;
+                        int contributor = 0, last_contributor = 0;
+                        for (int e = 0; e < n; e++) {
+                            contributor++;
+                            const int g = list[e];
+                            float dx, dy, G, alpha;
+                            if (!pair_alpha(sp.px[g], sp.py[g], sp.conx[g], sp.cony[g], sp.conz[g], sp.opac[g], pxf, pyf, dx, dy, G, alpha)) continue;
+                            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                            if (test_T < T_EPS) break;
+                            T = test_T;
+                            last_contributor = contributor;
+                        }
+                        // backward replay (backward.cu:536-636) with the one-hot scalar recurrence
+                        float S = 0.f, last_alpha = 0.f, last_g = 0.f;
+                        for (int e = last_contributor - 1; e >= 0; e--) {
+                            const int g = list[e];
+                            float dx, dy, G, alpha;
+                            if (!pair_alpha(sp.px[g], sp.py[g], sp.conx[g], sp.cony[g], sp.conz[g], sp.opac[g], pxf, pyf, dx, dy, G, alpha)) continue;
+                            T = T / (1.f - alpha);
+                            const float c = alpha * T;                       // rendered value of channel g at this pixel
+                            // GT lookup in the ROI patch of (view, joint g)
+                            const int rx = px - s_roi[v][g][0], ry = py - s_roi[v][g][1];
+                            float gt = 0.f;
+                            if (rx >= 0 && ry >= 0 && rx < s_roi[v][g][2] && ry < s_roi[v][g][3])
+                                gt = __ldg(p.roi_data + s_roi_off[v][g] + (long long)ry * s_roi[v][g][2] + rx);
+                            const float err = c - gt;
+                            const float gpix = 2.f * err;                    // unscaled dL/drender (x 1/N later)
+                            S = last_alpha * last_g + (1.f - last_alpha) * S;
+                            last_g = gpix;
+                            last_alpha = alpha;
+                            const int u = e - c0;
+                            if (u >= 0 && u < FAST) {
+                                if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
+                                const float dL_dalpha = (gpix - S) * T;
+                                const float dL_dG = sp.opac[g] * dL_dalpha;
+                                const float gdx = G * dx, gdy = G * dy;
+                                const float dG_ddelx = -gdx * sp.conx[g] - gdy * sp.cony[g];
+                                const float dG_ddely = -gdy * sp.conz[g] - gdx * sp.cony[g];
+                                const float w0 = dL_dG * dG_ddelx * ddelx_dx, w1 = dL_dG * dG_ddely * ddely_dy;
+                                const float w2 = -0.5f * gdx * dx * dL_dG, w3 = -0.5f * gdx * dy * dL_dG, w4 = -0.5f * gdy * dy * dL_dG;
+                                const float w5 = G * dL_dalpha;
+#pragma unroll
+                                for (int uu = 0; uu < FAST; uu++)
+                                    if (u == uu) { accv[uu][0] += w0; accv[uu][1] += w1; accv[uu][2] += w2; accv[uu][3] += w3; accv[uu][4] += w4; accv[uu][5] += w5; }
+                            }
+                        }
+                    }
+                    // one reduction per (tile, entry): 8 values (6 used) in 9 shuffles
+#pragma unroll
+                    for (int u = 0; u < FAST; u++) {
+                        if (c0 + u < n) {     // warp-uniform
+                            float r8[8] = {accv[u][0], accv[u][1], accv[u][2], accv[u][3], accv[u][4], accv[u][5], 0.f, 0.f};
+                            const float tot = warp_multi_reduce<8>(r8, lane);
+                            const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
+                            if ((lane & 3) == 0 && idx < NPART) d_part[((size_t)k * RCAP + e0 + c0 + u) * NPART + idx] = tot;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < SLOTS; kk++) if (k == kk) { lsum[kk] += my_lsum; lcnt[kk] += my_cnt; }
+            }
+#pragma unroll
+            for (int k = 0; k < SLOTS; k++) {
+                float a = lsum[k]; int c = lcnt[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); c += __shfl_xor_sync(0xFFFFFFFFu, c, o); }
+                if (lane == 0) { s_lsum[k][warp] = a; if (c) atomicAdd(&s_cnt[k], c); }
+            }
+        }
+        __syncthreads();
+
+        // ============ phase D: per-Gaussian backward chain + gradient bookkeeping ============
+        if (tid < SLOTS * J) {
+            const int k = tid / J, j = tid % J;
+            const int v = (step * acc + k) % V;
+            const SlotSplats& sp = s_sp[k];
+            const float invN = 1.0f / (float)(s_ngt[v] + s_cnt[k]);      // mean over the loss mask
+            float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gop = 0.f;
+            if (sp.tiles[j] > 0) {
+                float s6[NPART] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const int o0 = (j == 0) ? 0 : sp.offs[j - 1], o1 = min((int)sp.offs[j], s_R[k]);
+                for (int o = o0; o < o1; o++) {
+                    const float* pp = d_part + ((size_t)k * RCAP + d_inv[(size_t)k * RCAP + o]) * NPART;
+#pragma unroll
+                    for (int q = 0; q < NPART; q++) s6[q] += pp[q];
+                }
+#pragma unroll
+                for (int q = 0; q < NPART; q++) s6[q] *= invN;
+                const SplatGrad sg = gaussian_backward(
+                    s_xyz[3 * j], s_xyz[3 * j + 1], s_xyz[3 * j + 2], &s_cov3d[6 * j], true,
+                    s_act_scale[3 * j], s_act_scale[3 * j + 1], s_act_scale[3 * j + 2], 1.0f,
+                    s_act_q[4 * j], s_act_q[4 * j + 1], s_act_q[4 * j + 2], s_act_q[4 * j + 3],
+                    s_view[v], s_proj[v], s_fx[v], s_fy[v], s_tfx[v], s_tfy[v],
+                    s6[0], s6[1], s6[2], s6[3], s6[4], 0.f, true);
+                gm[0] = sg.dmean[0]; gm[1] = sg.dmean[1]; gm[2] = sg.dmean[2];
+                // exp backward
+                gs[0] = sg.dscale[0] * s_act_scale[3 * j]; gs[1] = sg.dscale[1] * s_act_scale[3 * j + 1]; gs[2] = sg.dscale[2] * s_act_scale[3 * j + 2];
+                // F.normalize backward: (g - y (y.g)) / |x|
+                const float dotq = sg.drot[0] * s_act_q[4 * j] + sg.drot[1] * s_act_q[4 * j + 1] + sg.drot[2] * s_act_q[4 * j + 2] + sg.drot[3] * s_act_q[4 * j + 3];
+#pragma unroll
+                for (int c = 0; c < 4; c++) gq[c] = (sg.drot[c] - s_act_q[4 * j + c] * dotq) / s_act_qn[j];
+                // sigmoid backward
+                gop = s6[5] * s_act_op[j] * (1.f - s_act_op[j]);
+            }
+            // accumulated_grads[view] = raster gradient + lambda * limb-consistency gradient (added below)
+            s_accg[v][3 * j] = gm[0]; s_accg[v][3 * j + 1] = gm[1]; s_accg[v][3 * j + 2] = gm[2];
+            if (k == SLOTS - 1) {   // scaling / rotation / opacity grads: the LAST view of the group only (train.py:177-179)
+                s_grad[3 * J + 3 * j] = gs[0]; s_grad[3 * J + 3 * j + 1] = gs[1]; s_grad[3 * J + 3 * j + 2] = gs[2];
+#pragma unroll
+                for (int c = 0; c < 4; c++) s_grad[6 * J + 4 * j + c] = gq[c];
+                s_grad[10 * J + j] = gop;
+            }
+        }
+        __syncthreads();
+        // limb-consistency term: same xyz for every slot of the group => same gradient added to each slot's view
+        if (tid < SLOTS) {
+            const int k = tid, v = (step * acc + k) % V;
+            float cons = 0.f;
+            const bool last_of_view = (k + V >= SLOTS);      // V < SLOTS: several slots share a view, the last one wins
+            if (p.cfg.lambda_consistency != 0.f) {
+                for (int h = 0; h < 2; h++) {
+                    const int a0 = p.cfg.limb_pairs[4 * h], a1 = p.cfg.limb_pairs[4 * h + 1], b0 = p.cfg.limb_pairs[4 * h + 2], b1 = p.cfg.limb_pairs[4 * h + 3];
+                    float da[3], db[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { da[c] = s_xyz[3 * a0 + c] - s_xyz[3 * a1 + c]; db[c] = s_xyz[3 * b0 + c] - s_xyz[3 * b1 + c]; }
+                    const float la = sqrtf(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
+                    const float lb = sqrtf(db[0] * db[0] + db[1] * db[1] + db[2] * db[2]);
+                    const float diff = la - lb;
+                    cons += fabsf(diff);
+                    const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+                    const float lam = p.cfg.lambda_consistency;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float ga = (la > 0.f) ? lam * sgn * da[c] / la : 0.f;
+                        const float gb = (lb > 0.f) ? -lam * sgn * db[c] / lb : 0.f;
+                        if (last_of_view) {
+                            s_accg[v][3 * a0 + c] += ga; s_accg[v][3 * a1 + c] -= ga;
+                            s_accg[v][3 * b0 + c] += gb; s_accg[v][3 * b1 + c] -= gb;
+                        }
+                    }
+                }
+            }
+            if (k == SLOTS - 1) {
+                float a = 0.f;
+                for (int w = 0; w < OPT_WARPS; w++) a += s_lsum[k][w];
+                last_loss = (a + s_sgt2[v]) / (float)(s_ngt[v] + s_cnt[k]) + p.cfg.lambda_consistency * cons;
+                if (p.final_loss && step == p.n_steps - 1) p.final_loss[frame] = last_loss;
+            }
+        }
+        __syncthreads();
+        // ============ phase E: Adam (torch.optim.Adam, foreach path; train.py:215-222) ============
+        if (tid < J * 11) {
+            const int i = tid;
+            float g, neg_step;
+            float* param;
+            if (i < 3 * J) {                 // xyz: mean over the V slots (stale / zero slots included)
+                float a = 0.f;
+                for (int v = 0; v < V; v++) a += s_accg[v][i];
+                g = a / (float)V;
+                neg_step = tab.neg_step_xyz[step]; param = &s_xyz[i];
+            } else if (i < 6 * J) { g = s_grad[i]; neg_step = tab.neg_step_scaling[step]; param = &s_scal[i - 3 * J]; }
+            else if (i < 10 * J) { g = s_grad[i]; neg_step = tab.neg_step_rotation[step]; param = &s_rot[i - 6 * J]; }
+            else { g = s_grad[i]; neg_step = tab.neg_step_opacity[step]; param = &s_opa[i - 10 * J]; }
+            const float m = fmaf(1.0f - p.cfg.beta1, g - s_m[i], s_m[i]);                 // lerp_(grad, 1-beta1)
+            const float vv = fmaf((1.0f - p.cfg.beta2) * g, g, s_v[i] * p.cfg.beta2);    // mul_(beta2).addcmul_(g, g, 1-beta2)
+            s_m[i] = m; s_v[i] = vv;
+            const float denom = sqrtf(vv) / tab.bc2_sqrt[step] + p.cfg.eps;
+            *param = fmaf(neg_step, m / denom, *param);                                   // addcdiv_(m, denom, -step_size)
+        }
+        __syncthreads();
+    }
+
+    // ---------------- write back ----------------
+    for (int i = tid; i < J * 3; i += OPT_THREADS) { p.xyz[(size_t)frame * J * 3 + i] = s_xyz[i]; p.scaling_raw[(size_t)frame * J * 3 + i] = s_scal[i]; }
+    for (int i = tid; i < J * 4; i += OPT_THREADS) p.rotation_raw[(size_t)frame * J * 4 + i] = s_rot[i];
+    for (int i = tid; i < J; i += OPT_THREADS) p.opacity_raw[(size_t)frame * J + i] = s_opa[i];
+    if (tid == 0 && p.status) p.status[frame] = s_status;
+    (void)last_loss;
+}
+
+static size_t opt_dyn_smem(int slots, int rcap) {
+    return (size_t)slots * rcap * (8 + 4 + 4 * NPART + 2 * 4);
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+extern "C" {
+
+size_t ssb_optimize_workspace_bytes(const ssb_opt_config* cfg, int n_frames) {
+    (void)cfg;
+    return (size_t)(n_frames > 0 ? n_frames : 1) * sizeof(int);     // per-frame status words
+}
+
+int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams, const double* lr_xyz_host,
+                        float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
+                        const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
+                        float* final_loss, void* workspace, void* stream_)
+{
+    if (!cfg || !cams || !lr_xyz_host || n_frames < 0) return SSB_ERR_INVALID;
+    if (cfg->J <= 0 || cfg->J > MAXJ || cfg->V <= 0 || cfg->V > MAXV || cams->n_views != cfg->V) return SSB_ERR_UNSUPPORTED;
+    if (cfg->accumulation_steps < 1 || cfg->accumulation_steps > MAX_SLOTS || cfg->accumulation_steps == 3) return SSB_ERR_UNSUPPORTED;
+    if (cfg->r_capacity < 32 || cfg->r_capacity > 1024 || (cfg->r_capacity & (cfg->r_capacity - 1))) return SSB_ERR_CAPACITY;
+    const int n_steps = cfg->iterations / cfg->accumulation_steps;   // trailing iterations never reach an optimiser step
+    if (n_steps > MAX_STEPS) return SSB_ERR_CAPACITY;
+    for (int i = 0; i < 8; i++) if (cfg->limb_pairs[i] < 0 || cfg->limb_pairs[i] >= cfg->J) return SSB_ERR_INVALID;
+    if (n_frames == 0) return SSB_OK;
+    if (!xyz || !scaling_raw || !rotation_raw || !opacity_raw || !roi_rect || !roi_offset || !roi_data || !workspace) return SSB_ERR_INVALID;
+
+    // Host scalars exactly as torch.optim.Adam's foreach path computes them (python floats = fp64),
+    // then rounded to fp32 where torch hands them to an fp32 tensor op.
+    StepTable tab;
+    for (int s = 0; s < n_steps; s++) {
+        const double step = (double)(s + 1);
+        const double bc1 = 1.0 - std::pow((double)cfg->beta1, step);
+        const double bc2 = 1.0 - std::pow((double)cfg->beta2, step);
+        const int it = (s + 1) * cfg->accumulation_steps;          // lr is taken at the stepping iteration
+        tab.neg_step_xyz[s] = (float)(-(lr_xyz_host[it] / bc1));
+        tab.neg_step_scaling[s] = (float)(-((double)cfg->lr_scaling / bc1));
+        tab.neg_step_rotation[s] = (float)(-((double)cfg->lr_rotation / bc1));
+        tab.neg_step_opacity[s] = (float)(-((double)cfg->lr_opacity / bc1));
+        tab.bc2_sqrt[s] = (float)std::sqrt(bc2);
+    }
+    OptParams p;
+    p.cfg = *cfg; p.cams = *cams; p.n_frames = n_frames; p.n_steps = n_steps;
+    p.xyz = xyz; p.scaling_raw = scaling_raw; p.rotation_raw = rotation_raw; p.opacity_raw = opacity_raw;
+    p.roi_rect = roi_rect; p.roi_offset = roi_offset; p.roi_data = roi_data; p.final_loss = final_loss;
+    p.status = (int*)workspace;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int slots = cfg->accumulation_steps;
+    const size_t smem = opt_dyn_smem(slots, cfg->r_capacity);
+#define SSB_LAUNCH_OPT(S)                                                                                         \
+    {                                                                                                             \
+        if (cudaFuncSetAttribute(optimize_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+            return ssb_set_cuda_error(cudaGetLastError());                                                        \
+        optimize_kernel<S><<<n_frames, OPT_THREADS, smem, stream>>>(p, tab);                                      \
+    }
+    switch (slots) {
+        case 1: SSB_LAUNCH_OPT(1) break;
+        case 2: SSB_LAUNCH_OPT(2) break;
+        case 4: SSB_LAUNCH_OPT(4) break;
+        default: return SSB_ERR_UNSUPPORTED;
+    }
+    return ssb_set_cuda_error(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""Pseudo-ground-truth heatmaps as ROI patches (per-frame setup feeding the hot path).
+
+The reference builds, per frame, V dense ``[J,H,W]`` float32 heatmaps with one
+cupy ``gaussian_filter`` call per (view, joint) on a megapixel image
+(utils/general_utils.py:175-304).  Only a ``(2r_y+1) x (2r_x+1)`` window around each
+detection is non-zero, so this module produces exactly those windows ("ROIs") and the
+fused optimiser consumes them directly; ``rois_to_dense`` re-creates the dense tensor
+for the drop-in (dense) API and for the parity tests.
+
+Semantics kept literally from the reference:
+  * sigma from the *initial* Gaussians' covariance pushed through ``T = R_w2c @ J`` with J
+    row-wise -- which is NOT the rasteriser's EWA form (general_utils.py:224-246),
+    +0.3 dilation, ``lambda = mid +- sqrt(max(0.1, mid^2 - det))``, ``sigma_y = sqrt(lambda1)`` on
+    axis 0 and ``sigma_x = sqrt(lambda2)`` on axis 1 (general_utils.py:248-265);
+  * peak at ``(clamp(int(v)), clamp(int(u)))`` with value 255 (general_utils.py:275-284);
+  * separable Gaussian, ``truncate=4`` => half-width ``int(4*sigma+0.5)``, ``mode='reflect'``
+    (cupyx/scipy ``gaussian_filter`` defaults, general_utils.py:289);
+  * per-channel min-max normalisation with the +1e-8 (general_utils.py:300-304).
+The filter arithmetic follows scipy.ndimage (float64 accumulation, float32 storage
+between the two passes); cupy's float32 accumulation is not reproducible here --
+"parity unpinned" for this setup step, as SURVEY.md section 8c records.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def _rotation_matrices(q):
+    """build_rotation, utils/general_utils.py:87-108 (normalises q)."""
+    q = q / np.sqrt((q * q).sum(1, keepdims=True))
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.zeros((q.shape[0], 3, 3), np.float32)
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - r * z); R[:, 0, 2] = 2 * (x * z + r * y)
+    R[:, 1, 0] = 2 * (x * y + r * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - r * x)
+    R[:, 2, 0] = 2 * (x * z - r * y); R[:, 2, 1] = 2 * (y * z + r * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def covariance_3d(scaling_raw, rotation, scaling_modifier=1.0):
+    """GaussianModel.get_covariance -> unpack_covariance: Sigma = (R S)(R S)^T
+    (scene/gaussian_model.py:33-37, utils/general_utils.py:110-119,144-165)."""
+    s = np.exp(scaling_raw.astype(np.float32)) * np.float32(scaling_modifier)
+    R = _rotation_matrices(rotation.astype(np.float32))
+    L = R * s[:, None, :]
+    return (L @ L.transpose(0, 2, 1)).astype(np.float32)
+
+
+def heatmap_sigmas(xyz, cams, cov3d):
+    """(sigma_y, sigma_x), each [V,J] float32 -- general_utils.py:199-265 in numpy float32."""
+    f32 = np.float32
+    V, J = len(cams), xyz.shape[0]
+    xyz = xyz.astype(f32)
+    s1 = np.zeros((V, J), f32); s2 = np.zeros((V, J), f32)
+    hom = np.concatenate([xyz, np.ones((J, 1), f32)], 1)
+    for v, cam in enumerate(cams):
+        view = cam.world_view_transform.T.astype(f32)          # = W2C
+        tanx, tany = f32(np.tan(f32(cam.FoVx * 0.5))), f32(np.tan(f32(cam.FoVy * 0.5)))
+        fx = f32(cam.image_width) / (f32(2.0) * tanx)
+        fy = f32(cam.image_height) / (f32(2.0) * tany)
+        t = (view @ hom.T).T[:, :3].astype(f32)
+        limx, limy = f32(1.3) * tanx, f32(1.3) * tany
+        txtz, tytz = t[:, 0] / t[:, 2], t[:, 1] / t[:, 2]
+        t[:, 0] = np.clip(txtz, -limx, limx) * t[:, 2]
+        t[:, 1] = np.clip(tytz, -limy, limy) * t[:, 2]
+        Jm = np.zeros((J, 3, 3), f32)
+        Jm[:, 0, 0] = fx / t[:, 2]; Jm[:, 0, 2] = -(fx * t[:, 0]) / t[:, 2] ** 2
+        Jm[:, 1, 1] = fy / t[:, 2]; Jm[:, 1, 2] = -(fy * t[:, 1]) / t[:, 2] ** 2
+        T = view[None, :3, :3] @ Jm
+        cov = T.transpose(0, 2, 1) @ cov3d.transpose(0, 2, 1) @ T
+        cx = cov[:, 0, 0] + f32(0.3); cy = cov[:, 0, 1]; cz = cov[:, 1, 1] + f32(0.3)
+        det = cx * cz - cy * cy
+        mid = f32(0.5) * (cx + cz)
+        root = np.sqrt(np.maximum(f32(0.1), mid * mid - det))
+        s1[v] = np.sqrt(mid + root)
+        s2[v] = np.sqrt(mid - root)
+    return s1, s2
+
+
+def _gauss_weights(sigma, radius):
+    """scipy.ndimage._gaussian_kernel1d (order 0)."""
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return phi / phi.sum()
+
+
+def _filtered_delta_1d(n, pos, sigma, amplitude, dtype):
+    """Response of scipy's ``correlate1d(mode='reflect')`` with a truncated Gaussian to a delta of
+    ``amplitude`` at ``pos`` on an axis of length ``n``; returns (start, values) of its support."""
+    radius = int(4.0 * float(sigma) + 0.5)
+    w = _gauss_weights(float(sigma), radius)
+    lo, hi = max(0, pos - radius), min(n - 1, pos + radius)
+    idx = np.arange(lo, hi + 1)
+    out = np.zeros(idx.shape[0], np.float64)
+    # out[i] = sum_k w[k] * in[reflect(i + k - radius)]; 'reflect' = (d c b a | a b c d | d c b a)
+    for k in range(2 * radius + 1):
+        src = idx + k - radius
+        src = np.where(src < 0, -src - 1, src)
+        src = np.where(src >= n, 2 * n - 1 - src, src)
+        out += np.where(src == pos, w[k] * amplitude, 0.0)
+    return lo, out.astype(dtype)
+
+
+@dataclass
+class HeatmapROIs:
+    """Packed ROI patches of one frame.  rect[v,j] = (x0, y0, w, h); the patch of (v,j) is
+    ``data[offset[v,j] : offset[v,j] + w*h]`` row-major; values are the normalised heatmap."""
+    rect: np.ndarray      # [V,J,4] int32
+    offset: np.ndarray    # [V,J]   int64
+    data: np.ndarray      # [total] float32
+    sizes: list           # [(W,H)] per view
+
+    def patch(self, v, j):
+        x0, y0, w, h = self.rect[v, j]
+        o = self.offset[v, j]
+        return self.data[o:o + w * h].reshape(h, w)
+
+
+def generate_heatmap_rois(xyz_init, poses_2d, cams, scaling_raw, rotation, scaling_modifier=1.0):
+    """ROI form of generate_heatmaps (utils/general_utils.py:175-297)."""
+    f32 = np.float32
+    V, J = len(cams), xyz_init.shape[0]
+    cov3d = covariance_3d(scaling_raw, rotation, scaling_modifier)
+    s1, s2 = heatmap_sigmas(xyz_init, cams, cov3d)
+    rect = np.zeros((V, J, 4), np.int32); offset = np.zeros((V, J), np.int64)
+    chunks, total = [], 0
+    for v, cam in enumerate(cams):
+        W, H = cam.image_width, cam.image_height
+        for j in range(J):
+            xc = int(np.clip(int(poses_2d[v, j, 0]), 0, W - 1))    # .long() truncates toward zero
+            yc = int(np.clip(int(poses_2d[v, j, 1]), 0, H - 1))
+            y0, col = _filtered_delta_1d(H, yc, s1[v, j], 255.0, f32)      # pass 1 (axis 0), stored float32
+            x0, row = _filtered_delta_1d(W, xc, s2[v, j], 1.0, np.float64)  # pass 2 weights
+            patch = (col.astype(np.float64)[:, None] * row[None, :]).astype(f32)
+            mx, mn = patch.max(), f32(0.0) if patch.size < W * H else patch.min()
+            patch = ((patch - mn) / (mx - mn + f32(1e-8))).astype(f32)
+            rect[v, j] = (x0, y0, patch.shape[1], patch.shape[0])
+            offset[v, j] = total
+            chunks.append(patch.reshape(-1))
+            total += patch.size
+    return HeatmapROIs(rect=rect, offset=offset, data=np.concatenate(chunks), sizes=[(c.image_width, c.image_height) for c in cams])
+
+
+def rois_to_dense(rois: HeatmapROIs, v):
+    """Dense ``[J,H,W]`` float32 heatmap of view v, as the reference stores it."""
+    W, H = rois.sizes[v]
+    J = rois.rect.shape[1]
+    out = np.zeros((J, H, W), np.float32)
+    for j in range(J):
+        x0, y0, w, h = rois.rect[v, j]
+        out[j, y0:y0 + h, x0:x0 + w] = rois.patch(v, j)
+    return out
