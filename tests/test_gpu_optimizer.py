@@ -1,0 +1,98 @@
+"""The fused per-frame optimiser against the restated train.py loop: on the C oracle (CPU, short runs), on the
+golden final poses produced by the UNMODIFIED reference kernels (500 iterations), and through size-independent
+properties at BASELINE.json's full sizes (determinism, batch invariance, frame independence).
+
+Tolerance (north-star: final joints / MPJPE within 0.1 mm): MPJPE always within 0.1 mm; per-joint positions within
+0.1 mm wherever the reference itself is reproducible to that level (occlusion-person: rotation lr 0).  For the
+configs whose rotation group is driven by Adam with eps=1e-15 on noise-level gradients the reference's OWN two-run
+spread (its backward uses unordered fp32 atomics) is 0.2-0.7 mm per joint (stored in the fixtures), so the
+per-joint bound there is a small multiple of that measured spread."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as opipe
+from skelsplat_b200 import configs, synthetic, heatmaps, trainer
+from skelsplat_b200.cameras import cameras_extent
+from tests.util import small_config, golden_path, have_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def oracle_loop(cfg, seq, fi, iterations, trace=None):
+    fr = seq.frames[fi]
+    _, scal0, rot0, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+    rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal0[0], rot0[0])
+    dense = [torch.from_numpy(heatmaps.rois_to_dense(rois, v)) for v in range(cfg.nviews)]
+    return opipe.optimise_frame(fr, seq.cameras, cfg, cameras_extent(seq.cameras), dense, backend="oracle", device="cpu",
+                                iterations=iterations, trace=trace)
+
+
+@pytest.mark.parametrize("name", ["h36m", "h36m-occ", "panoptic", "occlusion-person", "occlusion-person-8v"])
+def test_short_run_matches_the_oracle_loop(name):
+    """24 iterations = 6 Adam steps (covers the stale/zero gradient slots of the 8-view rig)."""
+    cfg = small_config(configs.get_config(name))
+    seq = synthetic.make_sequence(cfg, 2, seed=12)
+    mine = trainer.optimize_sequence(seq, DEV, iterations=24)
+    for fi in range(2):
+        ref = oracle_loop(cfg, seq, fi, 24)
+        moved = np.linalg.norm(ref - seq.frames[fi].pose_3d_init, axis=-1).max()
+        assert moved > 1.0                                    # the optimiser actually moved the joints
+        assert np.linalg.norm(mine[fi] - ref, axis=-1).max() < 0.02, name
+
+
+@pytest.mark.parametrize("name", ["h36m", "h36m-occ", "panoptic", "occlusion-person"])
+def test_full_run_against_reference_golden(name):
+    if not have_golden(f"opt_{name}.npz"):
+        pytest.skip("golden fixture missing")
+    G = np.load(golden_path(f"opt_{name}.npz"))
+    cfg = configs.get_config(name)
+    seq = synthetic.make_sequence(cfg, int(G["n_frames"]), seed=int(G["seed"]))
+    assert np.allclose(np.stack([f.pose_3d_init for f in seq.frames]), G["init_xyz"])      # same synthetic inputs
+    mine = trainer.optimize_sequence(seq, DEV, iterations=int(G["iterations"]))
+    ref, gt = G["ref_xyz"], G["gt_xyz"]
+    assert abs(trainer.mpjpe(mine, gt) - trainer.mpjpe(ref, gt)) < 0.1                     # MPJPE within 0.1 mm
+    dev = np.linalg.norm(mine - ref, axis=-1)
+    spread = float(np.linalg.norm(G["ref_xyz_frame0_run2"] - ref[0], axis=-1).max())       # the reference vs itself
+    assert dev.max() < max(0.1, 6.0 * spread), (name, dev.max(), spread)
+    assert np.median(dev) < 0.1
+
+
+def test_full_size_properties():
+    cfg = configs.H36M
+    seq = synthetic.make_sequence(cfg, 6, seed=21)
+    a = trainer.optimize_sequence(seq, DEV)
+    b = trainer.optimize_sequence(seq, DEV)
+    assert np.array_equal(a, b)                                                            # deterministic (no atomics)
+    sub = synthetic.Sequence(cfg=cfg, cameras=seq.cameras, frames=[seq.frames[4], seq.frames[1]])
+    c = trainer.optimize_sequence(sub, DEV)
+    assert np.array_equal(c[0], a[4]) and np.array_equal(c[1], a[1])                       # frames are independent
+    assert np.isfinite(a).all()
+    gt = np.stack([f.pose_3d_gt for f in seq.frames]); init = np.stack([f.pose_3d_init for f in seq.frames])
+    assert trainer.mpjpe(a, gt) < trainer.mpjpe(init, gt) + 2.0
+
+
+def test_loss_decreases_and_is_reported():
+    cfg = configs.H36M_OCC
+    seq = synthetic.make_sequence(cfg, 4, seed=3)
+    poses_init = np.stack([f.pose_3d_init for f in seq.frames]); poses_2d = np.stack([f.poses_2d for f in seq.frames])
+    host = trainer.pack_host(cfg, seq.cameras, poses_init, poses_2d)
+    first = trainer.optimize_packed(trainer.pack_sequence(cfg, seq.cameras, poses_init, poses_2d, DEV, host=host), iterations=4)[1].cpu().numpy()
+    last = trainer.optimize_packed(trainer.pack_sequence(cfg, seq.cameras, poses_init, poses_2d, DEV, host=host))[1].cpu().numpy()
+    assert (last < first).all() and (last > 0).all()
+
+
+def test_capacity_overflow_is_reported():
+    cfg = configs.PANOPTIC
+    seq = synthetic.make_sequence(cfg, 1, seed=0)
+    with pytest.raises(Exception, match="r_capacity"):
+        trainer.optimize_sequence(seq, DEV, iterations=8, r_capacity=64)
+
+
+def test_unsupported_loss_fails_loudly():
+    from dataclasses import replace
+    cfg = replace(configs.H36M, loss_function="l1")
+    seq = synthetic.make_sequence(cfg, 1, seed=0)
+    with pytest.raises(NotImplementedError):
+        trainer.optimize_sequence(seq, DEV, iterations=4)

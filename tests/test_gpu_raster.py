@@ -1,0 +1,214 @@
+"""Parity of the CUDA dense rasteriser (through the C ABI) with the C oracle, the golden fixtures of the
+reference kernels and -- when oracle/_ref is present on the box -- the reference kernels themselves.
+Bar: tile keys / sort order / ranges / radii / per-Gaussian state BIT-EXACT; image and gradients <= 1e-5
+relative (fp32; relative to the tensor's max magnitude, gradients being sums of mixed-sign terms)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rast
+from skelsplat_b200 import configs, synthetic
+from skelsplat_b200 import rasterizer as R
+from tests.util import small_config, raster_case, relerr, golden_path, have_golden, synthetic_dL
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+INT_KEYS = ("tiles_touched", "point_offsets", "keys_unsorted", "vals_unsorted", "keys_sorted", "point_list", "ranges")
+F32_KEYS = ("depths", "means2D", "conic_opacity", "cov3D")
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def mine_forward(case, vi, **kw):
+    W, H = int(case["dims"][vi, 0]), int(case["dims"][vi, 1])
+    P = case["means3D"].shape[0]
+    out = R.rasterize_batched(t(case["means3D"])[None], t(case["scales"])[None], t(case["rotations"])[None], t(case["opacities"]).reshape(1, P),
+                              t(case["features"]), t(case["viewmatrix"][vi])[None], t(case["projmatrix"][vi])[None], W, H,
+                              float(case["tanfov"][vi, 0]), float(case["tanfov"][vi, 1]), **kw)
+    torch.cuda.synchronize()
+    return out, W, H
+
+
+def mine_backward(case, vi, st, W, H, dL, dLinv=None):
+    P = case["means3D"].shape[0]
+    g = R.rasterize_batched_backward(st, t(case["means3D"])[None], t(case["scales"])[None], t(case["rotations"])[None], t(case["opacities"]).reshape(1, P),
+                                     t(case["features"]), t(case["viewmatrix"][vi])[None], t(case["projmatrix"][vi])[None], W, H,
+                                     float(case["tanfov"][vi, 0]), float(case["tanfov"][vi, 1]), t(dL)[None], None if dLinv is None else t(dLinv)[None])
+    torch.cuda.synchronize()
+    return {k: v[0].cpu().numpy() for k, v in g.items()}
+
+
+def oracle_forward(case, vi):
+    W, H = int(case["dims"][vi, 0]), int(case["dims"][vi, 1])
+    return rast.forward(case["means3D"], case["scales"], case["rotations"], case["opacities"], case["features"], case["viewmatrix"][vi],
+                        case["projmatrix"][vi], W, H, float(case["tanfov"][vi, 0]), float(case["tanfov"][vi, 1]))
+
+
+def assert_stages_equal(ms, ref, radii, ref_radii):
+    assert ms["R"] == ref["R"]
+    assert np.array_equal(radii, ref_radii)
+    for k in INT_KEYS:
+        assert np.array_equal(ms[k], ref[k]), k
+    vis = ref_radii > 0
+    for k in F32_KEYS:
+        assert np.array_equal(ms[k][vis].view(np.uint32), ref[k][vis].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("name", ["h36m", "panoptic", "occlusion-person"])
+@pytest.mark.parametrize("big", [True, False])
+def test_forward_and_backward_vs_oracle(name, big):
+    cfg = small_config(configs.get_config(name))
+    case = raster_case(cfg, seed=21, big=big)
+    for vi in range(2):
+        (color, radii, invd, st), W, H = mine_forward(case, vi)
+        of = oracle_forward(case, vi)
+        assert_stages_equal(st.parse(0), of, radii[0].cpu().numpy(), of["radii"])
+        assert relerr(color[0].cpu().numpy(), of["color"]) < TOL
+        assert relerr(invd[0].cpu().numpy(), of["invdepth"]) < TOL
+        rng = np.random.default_rng(vi)
+        dL = (rng.normal(size=of["color"].shape) * 1e-3).astype(np.float32)
+        dLinv = (rng.normal(size=of["invdepth"].shape) * 1e-3).astype(np.float32)
+        g = mine_backward(case, vi, st, W, H, dL, dLinv)
+        og = rast.backward(of, case["means3D"], case["scales"], case["rotations"], case["features"], case["viewmatrix"][vi], case["projmatrix"][vi],
+                           W, H, float(case["tanfov"][vi, 0]), float(case["tanfov"][vi, 1]), dL, dLinv)
+        for k, ok in (("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                      ("opacity", "dL_dopacity"), ("features", "dL_dcolors"), ("cov3D", "dL_dcov3D"), ("conic", "dL_dconic")):
+            assert relerr(g[k].reshape(-1), og[ok].reshape(-1)) < 2 * TOL, k
+
+
+@pytest.mark.parametrize("variant", ["h36m", "panoptic", "op"])
+def test_against_reference_golden(variant):
+    if not have_golden(f"raster_{variant}.npz"):
+        pytest.skip("golden fixture missing")
+    G = np.load(golden_path(f"raster_{variant}.npz"))
+    case = {k: G[k] for k in ("means3D", "scales", "rotations", "opacities", "features", "viewmatrix", "projmatrix", "campos", "dims", "tanfov")}
+    for vi in range(case["viewmatrix"].shape[0]):
+        (color, radii, invd, st), W, H = mine_forward(case, vi)
+        p = f"v{vi}_"
+        ref = {k: G[p + k] for k in INT_KEYS + F32_KEYS}
+        ref["R"] = int(G[p + "R"])
+        assert_stages_equal(st.parse(0), ref, radii[0].cpu().numpy(), G[p + "radii"])
+        assert relerr(color[0].cpu().numpy(), G[p + "color"]) < TOL
+        assert relerr(invd[0].cpu().numpy(), G[p + "invdepth"]) < TOL
+        g = mine_backward(case, vi, st, W, H, synthetic_dL(G[p + "color"].shape, vi), synthetic_dL(G[p + "invdepth"].shape, 10 + vi))
+        for k, rk in (("means3D", "dL_dmeans3D"), ("means2D", "dL_dmeans2D"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                      ("opacity", "dL_dopacity"), ("features", "dL_dcolors"), ("cov3D", "dL_dcov3D")):
+            spread = relerr(G[p + rk + "_run2"], G[p + rk])          # the reference's own atomics noise
+            assert relerr(g[k].reshape(-1), G[p + rk].reshape(-1)) < max(TOL, 4 * spread), k
+
+
+@pytest.mark.parametrize("name,variant", [("h36m", "h36m"), ("panoptic", "panoptic"), ("occlusion-person", "op")])
+def test_full_size_against_reference_kernels(name, variant):
+    """BASELINE.json full sizes, against the UNMODIFIED reference kernels running beside us."""
+    from oracle import ref_rasterizer as refr
+    if not refr.available(variant):
+        pytest.skip("oracle/_ref not present on this box")
+    cfg = configs.get_config(name)
+    case = raster_case(cfg, seed=31, n_views=cfg.nviews, big=False)
+    e = torch.Tensor([]); bg = torch.zeros(32, device=DEV)
+    J = cfg.n_joints
+    for vi in range(cfg.nviews):
+        (color, radii, invd, st), W, H = mine_forward(case, vi)
+        Rn, rcolor, rradii, geom, binning, img, rinvd = refr.rasterize_forward(
+            variant, bg, t(case["means3D"]), e, t(case["opacities"]).reshape(-1, 1), t(case["scales"]), t(case["rotations"]), 1.0, e,
+            t(case["viewmatrix"][vi]), t(case["projmatrix"][vi]), float(case["tanfov"][vi, 0]), float(case["tanfov"][vi, 1]), H, W,
+            t(case["features"]).reshape(J, 1, J), 0, t(case["campos"][vi]))
+        rs = refr.RefState(geom, binning, img, Rn, J, W, H, variant).parse()
+        assert_stages_equal(st.parse(0), rs, radii[0].cpu().numpy(), rradii.cpu().numpy())
+        assert relerr(color[0].cpu().numpy(), rcolor.cpu().numpy()) < TOL
+        # size-independent property: every element is written (no stale memory), untouched tiles are exactly zero
+        assert torch.isfinite(color).all()
+
+
+def test_batched_ragged_views_equal_single_view_calls():
+    """frames x views batching with per-view (W,H) and packed outputs == one call per view, bit for bit."""
+    cfg = small_config(configs.H36M)
+    seq = synthetic.make_sequence(cfg, 3, seed=8)
+    J, V, F = cfg.n_joints, cfg.nviews, 3
+    rng = np.random.default_rng(0)
+    means = np.stack([f.pose_3d_init for f in seq.frames]).astype(np.float32)
+    scales = np.exp(rng.uniform(3.5, 4.8, (F, J, 3))).astype(np.float32)
+    rots = rng.normal(size=(F, J, 4)).astype(np.float32); rots /= np.linalg.norm(rots, axis=-1, keepdims=True)
+    opac = rng.uniform(0.4, 1, (F, J)).astype(np.float32)
+    feats = np.eye(J, dtype=np.float32)
+    cams = seq.cameras
+    vm = np.stack([c.world_view_transform for c in cams]); pm = np.stack([c.full_proj_transform for c in cams])
+    dims = np.array([[c.image_width, c.image_height] for c in cams], np.int32)
+    tanfov = np.array([[c.tanfovx, c.tanfovy] for c in cams], np.float32)
+    Wm, Hm = int(dims[:, 0].max()), int(dims[:, 1].max())
+    sizes = [J * int(dims[b % V, 0]) * int(dims[b % V, 1]) for b in range(F * V)]
+    coff = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    isz = [int(dims[b % V, 0]) * int(dims[b % V, 1]) for b in range(F * V)]
+    ioff = np.concatenate([[0], np.cumsum(isz)[:-1]]).astype(np.int64)
+    out_color = torch.full((int(np.sum(sizes)),), float("nan"), device=DEV)
+    out_inv = torch.full((int(np.sum(isz)),), float("nan"), device=DEV)
+    _, radii, _, st = R.rasterize_batched(t(means), t(scales), t(rots), t(opac), t(feats), t(vm), t(pm), Wm, Hm, 0.0, 0.0,
+                                          dims=t(dims), tanfov=t(tanfov), color_offsets=t(coff), invdepth_offsets=t(ioff),
+                                          out_color=out_color, out_invdepth=out_inv)
+    dL_all = torch.from_numpy((rng.normal(size=int(np.sum(sizes))) * 1e-3).astype(np.float32)).to(DEV)
+    gb = R.rasterize_batched_backward(st, t(means), t(scales), t(rots), t(opac), t(feats), t(vm), t(pm), Wm, Hm, 0.0, 0.0, dL_all,
+                                      dims=t(dims), tanfov=t(tanfov), color_offsets=t(coff))
+    torch.cuda.synchronize()
+    assert not torch.isnan(out_color).any() and not torch.isnan(out_inv).any()       # every element written
+    for b in range(F * V):
+        f, v = b // V, b % V
+        W, H = int(dims[v, 0]), int(dims[v, 1])
+        c1, r1, i1, st1 = R.rasterize_batched(t(means[f])[None], t(scales[f])[None], t(rots[f])[None], t(opac[f])[None], t(feats),
+                                              t(vm[v])[None], t(pm[v])[None], W, H, float(tanfov[v, 0]), float(tanfov[v, 1]))
+        assert torch.equal(c1.reshape(-1), out_color[coff[b]:coff[b] + sizes[b]])
+        assert torch.equal(i1.reshape(-1), out_inv[ioff[b]:ioff[b] + isz[b]])
+        assert torch.equal(r1[0], radii[b])
+        g1 = R.rasterize_batched_backward(st1, t(means[f])[None], t(scales[f])[None], t(rots[f])[None], t(opac[f])[None], t(feats),
+                                          t(vm[v])[None], t(pm[v])[None], W, H, float(tanfov[v, 0]), float(tanfov[v, 1]),
+                                          dL_all[coff[b]:coff[b] + sizes[b]].reshape(1, J, H, W).contiguous())
+        for k in ("means3D", "scales", "rotations", "opacity"):
+            assert torch.equal(g1[k][0], gb[k][b]), k
+
+
+def test_backward_is_deterministic():
+    cfg = small_config(configs.PANOPTIC)
+    case = raster_case(cfg, seed=4)
+    (color, radii, invd, st), W, H = mine_forward(case, 0)
+    dL = np.random.default_rng(1).normal(size=color[0].shape).astype(np.float32)
+    a = mine_backward(case, 0, st, W, H, dL)
+    b = mine_backward(case, 0, st, W, H, dL)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_edge_cases():
+    cfg = small_config(configs.H36M)
+    case = raster_case(cfg, seed=9)
+    # (1) everything culled: behind the camera
+    c2 = dict(case); c2["means3D"] = (case["campos"][0][None] - 1000 * case["viewmatrix"][0][:3, 2][None]).repeat(cfg.n_joints, 0).astype(np.float32)
+    (color, radii, invd, st), W, H = mine_forward(c2, 0)
+    assert st.num_rendered() == 0 and not radii.any() and not color.any() and not invd.any()
+    g = mine_backward(c2, 0, st, W, H, np.ones((cfg.n_joints, H, W), np.float32))
+    assert all(not v.any() for v in g.values())
+    # (2) r_capacity overflow is flagged, never silent
+    (color, radii, invd, st), W, H = mine_forward(case, 0, r_capacity=32)
+    assert st.header()[2] == 1 and st.header()[7] > 32
+    with pytest.raises(Exception):
+        st.check()
+    # (3) precomputed 3D covariance gives the same image as scales+rotations (the cov3D is what the state stores)
+    (c_ref, _, _, st_ref), W, H = mine_forward(case, 0)
+    cov = st_ref.parse()["cov3D"]
+    P = cfg.n_joints
+    out = R.rasterize_batched(t(case["means3D"])[None], None, None, t(case["opacities"]).reshape(1, P), t(case["features"]),
+                              t(case["viewmatrix"][0])[None], t(case["projmatrix"][0])[None], W, H, float(case["tanfov"][0, 0]),
+                              float(case["tanfov"][0, 1]), cov3D_precomp=t(cov)[None])
+    assert torch.equal(out[0], c_ref)
+    # (4) generic channel count (C=3) and no inverse depth requested
+    feats3 = np.random.default_rng(0).uniform(size=(P, 3)).astype(np.float32)
+    c3 = dict(case); c3["features"] = feats3
+    (color3, _, invd3, st3), W, H = mine_forward(c3, 0, render_invdepth=False)
+    assert invd3 is None
+    assert relerr(color3[0].cpu().numpy(), oracle_forward(c3, 0)["color"]) < TOL
+    # (5) markVisible
+    rs = R.GaussianRasterizationSettings(H, W, 0.5, 0.5, torch.zeros(3, device=DEV), 1.0, t(case["viewmatrix"][0]), t(case["projmatrix"][0]), 0,
+                                         t(case["campos"][0]), False, False, False)
+    vis = R.GaussianRasterizer(rs).markVisible(t(np.concatenate([case["means3D"], c2["means3D"][:2]])))
+    assert vis[:P].all() and not vis[P:].any()

@@ -1,0 +1,145 @@
+"""Host-side logic (numpy / torch-CPU): cameras, DLT, GT heatmap ROIs, schedules, configs, sharding."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from skelsplat_b200 import cameras, configs, heatmaps, synthetic, trainer, triangulation
+from tests.util import small_config
+
+
+def test_projection_conventions():
+    """full_proj maps a world point to NDC such that ndc2Pix gives fx*x/z + cx - 0.5 and
+    the homogeneous w equals view-space z; matrices are stored transposed (scene/cameras.py:94-99)."""
+    seq = synthetic.make_sequence(configs.H36M, 1, seed=0)
+    X = seq.frames[0].pose_3d_gt
+    for cam in seq.cameras:
+        hom = np.concatenate([X, np.ones((X.shape[0], 1))], 1)
+        clip = hom @ cam.full_proj_transform.astype(np.float64)           # row-vector convention of the stored matrices
+        view = hom @ cam.world_view_transform.astype(np.float64)
+        assert np.allclose(clip[:, 3], view[:, 2], rtol=1e-6)
+        ndc = clip[:, :2] / clip[:, 3:4]
+        pix = ((ndc + 1.0) * np.array([cam.image_width, cam.image_height]) - 1.0) * 0.5
+        uv = synthetic.project(cam, X)
+        assert np.allclose(pix, uv - 0.5, atol=2e-2)
+        assert np.allclose(view[:, :3], X @ cam.R_w2c.T + cam.t, atol=1e-2)
+        assert math.isclose(cam.tanfovx, cam.image_width / (2 * cam.K[0, 0]), rel_tol=1e-12)
+        c = -cam.R_w2c.T @ cam.t
+        assert np.allclose(cam.camera_center, c, atol=1e-2)
+    ext = cameras.cameras_extent(seq.cameras)
+    centers = np.stack([-c.R_w2c.T @ c.t for c in seq.cameras])
+    assert math.isclose(ext, 1.1 * np.linalg.norm(centers - centers.mean(0), axis=1).max(), rel_tol=1e-5)
+
+
+def test_dlt_matches_reference_algorithm_and_recovers_noiseless_points():
+    cfg = configs.PANOPTIC
+    seq = synthetic.make_sequence(cfg, 3, seed=4)
+    P_list = [c.P3x4() for c in seq.cameras]
+    for fr in seq.frames:
+        det = np.stack([synthetic.project(c, fr.pose_3d_gt) for c in seq.cameras])
+        X = triangulation.triangulate_poses(P_list, det)
+        assert np.abs(X - fr.pose_3d_gt).max() < 1e-5
+        # per-joint loop exactly as triangulation.py:122-150
+        for j in range(cfg.n_joints):
+            A = []
+            for P, x in zip(P_list, fr.poses_2d[:, j]):
+                A.append(x[0] * P[2, :] - P[0, :]); A.append(x[1] * P[2, :] - P[1, :])
+            _, _, Vt = np.linalg.svd(np.array(A))
+            Xj = Vt[-1] / Vt[-1][3]
+            assert np.allclose(Xj[:3], fr.pose_3d_init[j], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["h36m", "occlusion-person"])
+def test_heatmap_rois_equal_the_dense_reference_procedure(name):
+    """ROI patches == delta(255) -> scipy gaussian_filter([s1,s2], truncate 4, reflect) -> per-channel min-max,
+    the restatement of utils/general_utils.py:175-304 (oracle/pipeline.generate_heatmaps_dense)."""
+    from oracle import pipeline as opipe
+    cfg = small_config(configs.get_config(name), factor=4)
+    seq = synthetic.make_sequence(cfg, 1, seed=2)
+    fr = seq.frames[0]
+    fr.poses_2d[0, 0] = [1.2, 3.9]                       # near a corner: exercises 'reflect' and the clamp
+    fr.poses_2d[1, 1] = [-5.0, 1e4]                      # outside the image: clamped to the border
+    g = opipe.RefGaussianModel(fr.pose_3d_init, cfg, 1.0, "cpu")
+    tcams = [opipe.TorchCamera(c, "cpu") for c in seq.cameras]
+    dense_ref = opipe.generate_heatmaps_dense(g, fr.poses_2d, tcams)
+    _, scal, rot, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+    rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal[0], rot[0])
+    for v in range(cfg.nviews):
+        mine = heatmaps.rois_to_dense(rois, v)
+        ref = dense_ref[str(v)].numpy()
+        assert mine.shape == ref.shape
+        assert np.array_equal(mine > 0, ref > 0)
+        assert np.abs(mine - ref).max() < 2e-6
+        assert mine.reshape(cfg.n_joints, -1).max(1).min() > 0.999
+
+
+def test_heatmap_sigma_uses_the_python_side_covariance_not_ewa():
+    """for the isotropic initial Gaussian the GT sigma has no perspective terms."""
+    cfg = configs.H36M
+    seq = synthetic.make_sequence(cfg, 1, seed=0)
+    fr = seq.frames[0]
+    _, scal, rot, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+    cov = heatmaps.covariance_3d(scal[0], rot[0])
+    s1, s2 = heatmaps.heatmap_sigmas(fr.pose_3d_init, seq.cameras, cov)
+    cam = seq.cameras[0]
+    z = (fr.pose_3d_init @ cam.R_w2c.T + cam.t)[:, 2]
+    sx = math.exp(3.0) * cam.K[0, 0] / z
+    lam = sx * sx + 0.3
+    # lambda = mid +- sqrt(max(0.1, ~0)) for an (almost) isotropic 2D covariance
+    assert np.allclose(s1[0] ** 2, lam + math.sqrt(0.1), rtol=5e-3)
+    assert np.allclose(s2[0] ** 2, lam - math.sqrt(0.1), rtol=5e-3)
+
+
+def test_lr_schedule_and_initial_state():
+    cfg = configs.H36M
+    tab = trainer.xyz_lr_table(cfg, 5000.0)
+    assert len(tab) == 501
+    a, b = cfg.position_lr_init * 5000.0, cfg.position_lr_final * 5000.0
+    for it in (1, 4, 250, 500):
+        t = it / 4000
+        assert math.isclose(tab[it], math.exp(math.log(a) * (1 - t) + math.log(b) * t), rel_tol=1e-12)
+    from oracle import pipeline as opipe
+    f = opipe.get_expon_lr_func(a, b, lr_delay_mult=0.0, max_steps=4000)
+    assert all(tab[i] == f(i) for i in range(1, 501))
+    poses = np.zeros((2, 15, 3))
+    xyz, scal, rot, opa = trainer.initial_raw_state(configs.OCCLUSION_PERSON, poses)
+    assert np.allclose(scal[0, [3, 6, 10, 11, 13, 14]], 3.75) and np.allclose(scal[0, [0, 1, 2]], 3.0)
+    xyz, scal, rot, opa = trainer.initial_raw_state(configs.H36M_OCC, np.zeros((1, 17, 3)))
+    assert np.allclose(scal, 3.0)                         # "h36m-occ" matches no branch: the 1.25 modifier is a no-op
+    assert np.all(rot[..., 0] == 1) and np.all(rot[..., 1:] == 0) and np.all(np.isinf(opa))
+
+
+def test_configs_match_the_shipped_yaml_values():
+    h, p, o = configs.H36M, configs.PANOPTIC, configs.OCCLUSION_PERSON
+    assert (h.n_joints, p.n_joints, o.n_joints) == (17, 19, 15)
+    assert h.position_lr_init == 0.0005 and p.position_lr_init == 0.005 and o.position_lr_init == 0.005
+    assert h.rotation_lr == 0.001 and o.rotation_lr == 0.0 and p.opacity_lr == 0.005 and h.opacity_lr == 0.0
+    assert h.iterations == 500 and h.accumulation_steps == 4 and h.lambda_consistency == 1e-5
+    assert h.image_sizes[0] == (1002, 1000) and p.image_sizes[0] == (1920, 1080) and o.image_sizes[0] == (1280, 720)
+    assert configs.get_config("occlusion-person-8v").nviews == 8
+
+
+def test_shard_bounds_partition_the_frames():
+    from skelsplat_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 64, 100001):
+        for w in (1, 2, 4, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_sequences_are_seeded_and_shaped():
+    for name in ("h36m", "h36m-occ", "panoptic", "occlusion-person", "occlusion-person-8v"):
+        cfg = configs.get_config(name)
+        a = synthetic.make_sequence(cfg, 2, seed=9); b = synthetic.make_sequence(cfg, 2, seed=9)
+        assert len(a.cameras) == cfg.nviews
+        assert a.frames[0].poses_2d.shape == (cfg.nviews, cfg.n_joints, 2)
+        assert np.array_equal(a.frames[1].pose_3d_init, b.frames[1].pose_3d_init)
+        err = np.linalg.norm(a.frames[0].pose_3d_init - a.frames[0].pose_3d_gt, axis=1).mean()
+        assert err < (200 if cfg.occluded else 60)
+        (l0, l1), (r0, r1) = cfg.limb_pairs[0], cfg.limb_pairs[1]
+        gt = a.frames[0].pose_3d_gt
+        assert math.isclose(np.linalg.norm(gt[l0] - gt[l1]), np.linalg.norm(gt[r0] - gt[r1]), rel_tol=1e-9)
