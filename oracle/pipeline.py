@@ -304,13 +304,17 @@ def generate_heatmaps_dense(gaussians, poses_2d, cams):
 
 
 def optimise_frame(frame, cams, cfg, spatial_lr_scale, heatmaps_dense, backend="ref", device="cuda",
-                   iterations=None, trace=None):
+                   iterations=None, trace=None, init_override=None):
     """One frame of train.py's frame loop.  heatmaps_dense: list of [J,H,W] tensors (one per
     view).  Returns the final xyz [J,3] (float32 numpy).  ``trace``: optional list that receives
     per-optimiser-step dicts (params after the step) for trajectory comparisons."""
     variant = VARIANT_OF[cfg.rendering]
     iterations = cfg.iterations if iterations is None else iterations
     gaussians = RefGaussianModel(frame.pose_3d_init, cfg, spatial_lr_scale, device)
+    if init_override is not None:       # tests only: start from a non-degenerate (anisotropic, rotated) state
+        with torch.no_grad():
+            gaussians._scaling.copy_(torch.as_tensor(init_override[0]).to(device))
+            gaussians._rotation.copy_(torch.as_tensor(init_override[1]).to(device))
     tcams = [TorchCamera(c, device) for c in cams]
     bg = torch.tensor([0, 0, 0], dtype=torch.float32, device=device)
     n_views = len(tcams)

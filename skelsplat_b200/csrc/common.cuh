@@ -173,6 +173,8 @@ __device__ __forceinline__ bool pair_alpha(float gpx, float gpy, float conx, flo
     t = __fmaf_rn(dx, __fmul_rn(dx, conx), t);
     const float power = __fmaf_rn(t, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cony)));
     if (power > 0.0f) return false;
+    // exact early-out: opac <= 1 and power < -5.55 imply opac*exp(power) <= 0.003888 < 1/255, the pair is skipped anyway
+    if (power < -5.55f && opac <= 1.0f) return false;
     G = expf(power);
     alpha = fminf(ALPHA_MAX, __fmul_rn(opac, G));
     return !(alpha < ALPHA_MIN);

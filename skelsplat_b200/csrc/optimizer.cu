@@ -27,8 +27,14 @@
 
 namespace ssb {
 
-constexpr int OPT_THREADS = 256;
+#ifndef SSB_OPT_THREADS
+#define SSB_OPT_THREADS 512
+#endif
+constexpr int OPT_THREADS = SSB_OPT_THREADS;
 constexpr int OPT_WARPS = OPT_THREADS / 32;
+#ifndef SSB_OPT_MIN_CTAS
+#define SSB_OPT_MIN_CTAS 2
+#endif
 constexpr int MAXJ = 20;
 constexpr int MAXV = 8;
 constexpr int MAX_SLOTS = 4;
@@ -77,14 +83,15 @@ __device__ __forceinline__ float warp_multi_reduce(float (&v)[V], int lane) {
 
 // Per-slot splat state (structure of arrays in shared memory).
 struct SlotSplats {
-    float px[MAXJ], py[MAXJ], conx[MAXJ], cony[MAXJ], conz[MAXJ], opac[MAXJ];
+    float4 geoA[MAXJ];                     // px, py, opacity, -
+    float4 geoB[MAXJ];                     // conic x, y, z, -
     uint32_t depth_bits[MAXJ];
     uint16_t rx0[MAXJ], ry0[MAXJ], rx1[MAXJ], ry1[MAXJ];
     uint16_t tiles[MAXJ], offs[MAXJ];      // tiles touched, inclusive scan
 };
 
 template <int SLOTS>
-__global__ void __launch_bounds__(OPT_THREADS, 2)
+__global__ void __launch_bounds__(OPT_THREADS, SSB_OPT_MIN_CTAS)
 optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ StepTable tab)
 {
     const int J = p.cfg.J, V = p.cfg.V, RCAP = p.cfg.r_capacity;
@@ -100,8 +107,9 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ float s_view[MAXV][16], s_proj[MAXV][16];
     __shared__ int s_W[MAXV], s_H[MAXV];
     __shared__ float s_tfx[MAXV], s_tfy[MAXV], s_fx[MAXV], s_fy[MAXV];
-    __shared__ int s_roi[MAXV][MAXJ][4];
-    __shared__ long long s_roi_off[MAXV][MAXJ];
+    __shared__ int4 s_roi[MAXV][MAXJ];          // x0, y0, w, h
+    __shared__ int s_roi_rel[MAXV][MAXJ];        // float offset relative to the frame's first patch
+    __shared__ long long s_roi_base;
     __shared__ int s_ngt[MAXV];            // sum_j #{gt > 0}
     __shared__ float s_sgt2[MAXV];         // sum_j sum gt^2
     __shared__ SlotSplats s_sp[SLOTS];
@@ -109,14 +117,15 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ float s_lsum[SLOTS][OPT_WARPS];
     __shared__ int s_status;
     extern __shared__ __align__(16) unsigned char dsm[];
-    // dynamic: per slot keys u64[RCAP] | sortvals u32[RCAP] | list u16[RCAP] | inv_pos u16[RCAP] | tile u16[RCAP] | start u16[RCAP] | partial f32[RCAP*NPART]
-    uint64_t* d_keys = reinterpret_cast<uint64_t*>(dsm);
-    uint32_t* d_vals = reinterpret_cast<uint32_t*>(d_keys + (size_t)SLOTS * RCAP);
-    float* d_part = reinterpret_cast<float*>(d_vals + (size_t)SLOTS * RCAP);
+    // dynamic, per slot: partial f32[RCAP*NPART] (24 B/entry) whose storage is first used by the sort's keys u64[RCAP]
+    // + payloads u32[RCAP] (dead once the tile lists exist) | list u16 | inv_pos u16 | tile u16 | start u16  => 32 B/entry
+    float* d_part = reinterpret_cast<float*>(dsm);
     uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)SLOTS * RCAP * NPART);
     uint16_t* d_inv = d_list + (size_t)SLOTS * RCAP;
     uint16_t* d_tile = d_inv + (size_t)SLOTS * RCAP;
     uint16_t* d_start = d_tile + (size_t)SLOTS * RCAP;
+#define SSB_KEYS(k) (reinterpret_cast<uint64_t*>(d_part + (size_t)(k) * RCAP * NPART))
+#define SSB_VALS(k) (reinterpret_cast<uint32_t*>(SSB_KEYS(k) + RCAP))
 
     // ---------------- load the frame ----------------
     for (int i = tid; i < J * 3; i += OPT_THREADS) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
@@ -136,18 +145,18 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     for (int i = tid; i < V * J; i += OPT_THREADS) {
         const int v = i / J, j = i % J;
         const size_t o = ((size_t)frame * V + v) * J + j;
-#pragma unroll
-        for (int k = 0; k < 4; k++) s_roi[v][j][k] = p.roi_rect[4 * o + k];
-        s_roi_off[v][j] = p.roi_offset[o];
+        s_roi[v][j] = make_int4(p.roi_rect[4 * o], p.roi_rect[4 * o + 1], p.roi_rect[4 * o + 2], p.roi_rect[4 * o + 3]);
+        s_roi_rel[v][j] = (int)(p.roi_offset[o] - p.roi_offset[(size_t)frame * V * J]);   // patches of a frame are packed together
     }
+    if (tid == 0) s_roi_base = p.roi_offset[(size_t)frame * V * J];
     if (tid == 0) s_status = 0;
     __syncthreads();
     // GT statistics of the loss mask: N_gt = #{gt>0}, S = sum gt^2 (per view; fixed-order per-warp sums)
     for (int v = 0; v < V; v++) {
         int cnt = 0; float sq = 0.f;
         for (int j = 0; j < J; j++) {
-            const int n = s_roi[v][j][2] * s_roi[v][j][3];
-            const float* d = p.roi_data + s_roi_off[v][j];
+            const int n = s_roi[v][j].z * s_roi[v][j].w;
+            const float* d = p.roi_data + s_roi_base + s_roi_rel[v][j];
             for (int i = tid; i < n; i += OPT_THREADS) { const float g = __ldg(d + i); if (g > 0.f) { cnt++; sq = fmaf(g, g, sq); } }
         }
 #pragma unroll
@@ -189,7 +198,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                              s_view[v], s_proj[v], s_W[v], s_H[v], s_tfx[v], s_tfy[v], s_fx[v], s_fy[v],
                                              p.cfg.antialiasing != 0);
             SlotSplats& sp = s_sp[k];
-            sp.px[j] = s.px; sp.py[j] = s.py; sp.conx[j] = s.conx; sp.cony[j] = s.cony; sp.conz[j] = s.conz; sp.opac[j] = s.opac;
+            sp.geoA[j] = make_float4(s.px, s.py, s.opac, 0.f);
+            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, 0.f);
             sp.depth_bits[j] = __float_as_uint(s.depth);
             sp.rx0[j] = (uint16_t)s.rect.x0; sp.ry0[j] = (uint16_t)s.rect.y0; sp.rx1[j] = (uint16_t)s.rect.x1; sp.ry1[j] = (uint16_t)s.rect.y1;
             sp.tiles[j] = (uint16_t)min(s.tiles, 65535u);
@@ -213,7 +223,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         }
         for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
             const int k = i / nsort, e = i - k * nsort;
-            d_keys[(size_t)k * RCAP + e] = ~0ull; d_vals[(size_t)k * RCAP + e] = 0xFFFFFFFFu;
+            SSB_KEYS(k)[e] = ~0ull; SSB_VALS(k)[e] = 0xFFFFFFFFu;
         }
         __syncthreads();
         if (tid < SLOTS * J) {
@@ -226,8 +236,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 for (uint32_t y = sp.ry0[j]; y < sp.ry1[j]; y++)
                     for (uint32_t x = sp.rx0[j]; x < sp.rx1[j]; x++) {
                         if (off < (uint32_t)s_R[k]) {
-                            d_keys[(size_t)k * RCAP + off] = ((uint64_t)(y * gx + x) << 32) | sp.depth_bits[j];
-                            d_vals[(size_t)k * RCAP + off] = (off << 10) | (uint32_t)j;
+                            SSB_KEYS(k)[off] = ((uint64_t)(y * gx + x) << 32) | sp.depth_bits[j];
+                            SSB_VALS(k)[off] = (off << 10) | (uint32_t)j;
                         }
                         off++;
                     }
@@ -241,8 +251,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                     const int k = i / nsort, e = i - k * nsort;
                     const int exj = e ^ jj;
                     if (exj > e) {
-                        uint64_t* K = d_keys + (size_t)k * RCAP;
-                        uint32_t* Vv = d_vals + (size_t)k * RCAP;
+                        uint64_t* K = SSB_KEYS(k);
+                        uint32_t* Vv = SSB_VALS(k);
                         const uint64_t ka = K[e], kb = K[exj];
                         const uint32_t va = Vv[e], vb = Vv[exj];
                         const bool a_gt_b = (ka > kb) || (ka == kb && va > vb);
@@ -255,14 +265,14 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
             const int k = i / nsort, e = i - k * nsort;
             if (e < s_R[k]) {
-                const uint32_t val = d_vals[(size_t)k * RCAP + e];
+                const uint32_t val = SSB_VALS(k)[e];
                 d_list[(size_t)k * RCAP + e] = (uint16_t)(val & 1023u);
                 d_inv[(size_t)k * RCAP + (val >> 10)] = (uint16_t)e;
             }
         }
         if (warp < SLOTS) {      // warp k: ordered compaction of the tile runs of slot k
             const int k = warp, R = s_R[k];
-            const uint64_t* K = d_keys + (size_t)k * RCAP;
+            const uint64_t* K = SSB_KEYS(k);
             int nact = 0;
             for (int base = 0; base < R; base += 32) {
                 const int i = base + lane;
@@ -304,77 +314,167 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const uint16_t* list = d_list + (size_t)k * RCAP + e0;
                 const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
                 const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+                const float* roi_base = p.roi_data + s_roi_base;
                 float my_lsum = 0.f; int my_cnt = 0;
-                for (int c0 = 0; c0 < n; c0 += FAST) {
+                const int lx = tx0 + (lane & 15), ly0 = ty0 + (lane >> 4);
+
+                // per (pixel, Gaussian) backward terms given alpha, G, T(before), the deltas and the unscaled dL/drender
+#define SSB_PAIR_BWD(ACC, A, B, dx, dy, G, alpha, Tb, gpix, S)                                              \
+                {                                                                                           \
+                    const float dL_dalpha = ((gpix) - (S)) * (Tb);                                          \
+                    const float dL_dG = (A).z * dL_dalpha;                                                  \
+                    const float gdx = (G) * (dx), gdy = (G) * (dy);                                         \
+                    const float dG_ddelx = -gdx * (B).x - gdy * (B).y;                                      \
+                    const float dG_ddely = -gdy * (B).z - gdx * (B).y;                                      \
+                    ACC[0] += dL_dG * dG_ddelx * ddelx_dx;                                                  \
+                    ACC[1] += dL_dG * dG_ddely * ddely_dy;                                                  \
+                    ACC[2] += -0.5f * gdx * (dx) * dL_dG;                                                   \
+                    ACC[3] += -0.5f * gdx * (dy) * dL_dG;                                                   \
+                    ACC[4] += -0.5f * gdy * (dy) * dL_dG;                                                   \
+                    ACC[5] += (G) * dL_dalpha;                                                              \
+                }
+                // GT value of channel g at pixel (px,py): ROI patch lookup (0 outside the patch)
+#define SSB_GT(gt, g, px, py)                                                                               \
+                {                                                                                           \
+                    const int4 roi = s_roi[v][g];                                                           \
+                    const int rx = (px) - roi.x, ry = (py) - roi.y;                                         \
+                    gt = 0.f;                                                                               \
+                    if ((unsigned)rx < (unsigned)roi.z && (unsigned)ry < (unsigned)roi.w)                   \
+                        gt = __ldg(roi_base + s_roi_rel[v][g] + ry * roi.z + rx);                           \
+                }
+
+                if (n <= FAST) {
+                    // ---------- fast path: the whole tile list lives in registers (alpha, G, T cached from the forward replay)
+                    int gid[FAST];
+#pragma unroll
+                    for (int u = 0; u < FAST; u++) gid[u] = (u < n) ? (int)list[u] : 0;
                     float accv[FAST][NPART];
 #pragma unroll
                     for (int u = 0; u < FAST; u++)
 #pragma unroll
                         for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
                     for (int pass = 0; pass < TILE / 2; pass++) {
-                        const int px = tx0 + (lane & 15), py = ty0 + 2 * pass + (lane >> 4);
-                        const bool inside = px < W && py < H;
-                        if (!inside) continue;          // no warp-collective operation inside the pass loop
+                        const int px = lx, py = ly0 + 2 * pass;
+                        if (!(px < W && py < H)) continue;          // no warp-collective operation inside the pass loop
                         const float pxf = (float)px, pyf = (float)py;
-                        // forward replay: final transmittance and last contributor (forward.cu:330-386)
+                        float al[FAST], Gv[FAST], Tb[FAST];
+                        unsigned ok = 0u;
                         float T = 1.0f;
-                        int contributor = 0, last_contributor = 0;
-                        for (int e = 0; e < n; e++) {
-                            contributor++;
-                            const int g = list[e];
-                            float dx, dy, G, alpha;
-                            if (!pair_alpha(sp.px[g], sp.py[g], sp.conx[g], sp.cony[g], sp.conz[g], sp.opac[g], pxf, pyf, dx, dy, G, alpha)) continue;
-                            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                            if (test_T < T_EPS) break;
-                            T = test_T;
-                            last_contributor = contributor;
-                        }
-                        // backward replay (backward.cu:536-636) with the one-hot scalar recurrence
-                        float S = 0.f, last_alpha = 0.f, last_g = 0.f;
-                        for (int e = last_contributor - 1; e >= 0; e--) {
-                            const int g = list[e];
-                            float dx, dy, G, alpha;
-                            if (!pair_alpha(sp.px[g], sp.py[g], sp.conx[g], sp.cony[g], sp.conz[g], sp.opac[g], pxf, pyf, dx, dy, G, alpha)) continue;
-                            T = T / (1.f - alpha);
-                            const float c = alpha * T;                       // rendered value of channel g at this pixel
-                            // GT lookup in the ROI patch of (view, joint g)
-                            const int rx = px - s_roi[v][g][0], ry = py - s_roi[v][g][1];
-                            float gt = 0.f;
-                            if (rx >= 0 && ry >= 0 && rx < s_roi[v][g][2] && ry < s_roi[v][g][3])
-                                gt = __ldg(p.roi_data + s_roi_off[v][g] + (long long)ry * s_roi[v][g][2] + rx);
-                            const float err = c - gt;
-                            const float gpix = 2.f * err;                    // unscaled dL/drender (x 1/N later)
-                            S = last_alpha * last_g + (1.f - last_alpha) * S;
-                            last_g = gpix;
-                            last_alpha = alpha;
-                            const int u = e - c0;
-                            if (u >= 0 && u < FAST) {
-                                if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
-                                const float dL_dalpha = (gpix - S) * T;
-                                const float dL_dG = sp.opac[g] * dL_dalpha;
-                                const float gdx = G * dx, gdy = G * dy;
-                                const float dG_ddelx = -gdx * sp.conx[g] - gdy * sp.cony[g];
-                                const float dG_ddely = -gdy * sp.conz[g] - gdx * sp.cony[g];
-                                const float w0 = dL_dG * dG_ddelx * ddelx_dx, w1 = dL_dG * dG_ddely * ddely_dy;
-                                const float w2 = -0.5f * gdx * dx * dL_dG, w3 = -0.5f * gdx * dy * dL_dG, w4 = -0.5f * gdy * dy * dL_dG;
-                                const float w5 = G * dL_dalpha;
+                        bool done = false;
 #pragma unroll
-                                for (int uu = 0; uu < FAST; uu++)
-                                    if (u == uu) { accv[uu][0] += w0; accv[uu][1] += w1; accv[uu][2] += w2; accv[uu][3] += w3; accv[uu][4] += w4; accv[uu][5] += w5; }
+                        for (int u = 0; u < FAST; u++) {
+                            if (u < n && !done) {
+                                const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
+                                float dx, dy, G, alpha;
+                                if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) {
+                                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                                    if (test_T < T_EPS) done = true;
+                                    else { al[u] = alpha; Gv[u] = G; Tb[u] = T; ok |= 1u << u; T = test_T; }
+                                }
+                            }
+                        }
+                        // all GT loads of this pixel are issued before any is consumed (independent L2 hits in flight)
+                        float gtv[FAST];
+#pragma unroll
+                        for (int u = 0; u < FAST; u++) {
+                            gtv[u] = 0.f;
+                            if (ok & (1u << u)) { SSB_GT(gtv[u], gid[u], px, py); }
+                        }
+                        float S = 0.f, last_alpha = 0.f, last_g = 0.f;
+#pragma unroll
+                        for (int u = FAST - 1; u >= 0; u--) {
+                            if (ok & (1u << u)) {
+                                const int g = gid[u];
+                                const float4 A = sp.geoA[g], B = sp.geoB[g];
+                                const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
+                                const float c = al[u] * Tb[u];               // rendered value of channel g at this pixel
+                                const float gt = gtv[u];
+                                const float err = c - gt;
+                                const float gpix = 2.f * err;                // unscaled dL/drender (x 1/N later)
+                                S = last_alpha * last_g + (1.f - last_alpha) * S;
+                                last_g = gpix; last_alpha = al[u];
+                                if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
+                                SSB_PAIR_BWD(accv[u], A, B, dx, dy, Gv[u], al[u], Tb[u], gpix, S);
                             }
                         }
                     }
                     // one reduction per (tile, entry): 8 values (6 used) in 9 shuffles
 #pragma unroll
                     for (int u = 0; u < FAST; u++) {
-                        if (c0 + u < n) {     // warp-uniform
+                        if (u < n) {     // warp-uniform
                             float r8[8] = {accv[u][0], accv[u][1], accv[u][2], accv[u][3], accv[u][4], accv[u][5], 0.f, 0.f};
                             const float tot = warp_multi_reduce<8>(r8, lane);
                             const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
-                            if ((lane & 3) == 0 && idx < NPART) d_part[((size_t)k * RCAP + e0 + c0 + u) * NPART + idx] = tot;
+                            if ((lane & 3) == 0 && idx < NPART) d_part[((size_t)k * RCAP + e0 + u) * NPART + idx] = tot;
+                        }
+                    }
+                } else {
+                    // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
+                    for (int c0 = 0; c0 < n; c0 += FAST) {
+                        float accv[FAST][NPART];
+#pragma unroll
+                        for (int u = 0; u < FAST; u++)
+#pragma unroll
+                            for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
+                        for (int pass = 0; pass < TILE / 2; pass++) {
+                            const int px = lx, py = ly0 + 2 * pass;
+                            if (!(px < W && py < H)) continue;
+                            const float pxf = (float)px, pyf = (float)py;
+                            // forward replay: final transmittance and last contributor (forward.cu:330-386)
+                            float T = 1.0f;
+                            int last_contributor = 0;
+                            for (int e = 0; e < n; e++) {
+                                const int g = list[e];
+                                const float4 A = sp.geoA[g], B = sp.geoB[g];
+                                float dx, dy, G, alpha;
+                                if (!pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) continue;
+                                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                                if (test_T < T_EPS) break;
+                                T = test_T;
+                                last_contributor = e + 1;
+                            }
+                            // backward replay (backward.cu:536-636) with the one-hot scalar recurrence
+                            float S = 0.f, last_alpha = 0.f, last_g = 0.f;
+                            for (int e = last_contributor - 1; e >= 0; e--) {
+                                const int g = list[e];
+                                const float4 A = sp.geoA[g], B = sp.geoB[g];
+                                float dx, dy, G, alpha;
+                                if (!pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) continue;
+                                T = T / (1.f - alpha);
+                                const float c = alpha * T;
+                                float gt;
+                                SSB_GT(gt, g, px, py);
+                                const float err = c - gt;
+                                const float gpix = 2.f * err;
+                                S = last_alpha * last_g + (1.f - last_alpha) * S;
+                                last_g = gpix; last_alpha = alpha;
+                                const int u = e - c0;
+                                if (u >= 0 && u < FAST) {
+                                    if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
+                                    float w[NPART] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                    SSB_PAIR_BWD(w, A, B, dx, dy, G, alpha, T, gpix, S);
+#pragma unroll
+                                    for (int uu = 0; uu < FAST; uu++)
+                                        if (u == uu) {
+#pragma unroll
+                                            for (int q = 0; q < NPART; q++) accv[uu][q] += w[q];
+                                        }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < FAST; u++) {
+                            if (c0 + u < n) {     // warp-uniform
+                                float r8[8] = {accv[u][0], accv[u][1], accv[u][2], accv[u][3], accv[u][4], accv[u][5], 0.f, 0.f};
+                                const float tot = warp_multi_reduce<8>(r8, lane);
+                                const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
+                                if ((lane & 3) == 0 && idx < NPART) d_part[((size_t)k * RCAP + e0 + c0 + u) * NPART + idx] = tot;
+                            }
                         }
                     }
                 }
+#undef SSB_PAIR_BWD
+#undef SSB_GT
 #pragma unroll
                 for (int kk = 0; kk < SLOTS; kk++) if (k == kk) { lsum[kk] += my_lsum; lcnt[kk] += my_cnt; }
             }
@@ -498,7 +598,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 }
 
 static size_t opt_dyn_smem(int slots, int rcap) {
-    return (size_t)slots * rcap * (8 + 4 + 4 * NPART + 2 * 4);
+    return (size_t)slots * rcap * (4 * NPART + 2 * 4);
 }
 
 }  // namespace ssb

@@ -7,10 +7,9 @@
 //                     keys, in-shared-memory bitonic sort, tile ranges + compact active-tile list.
 //                     Replaces preprocessCUDA + cub scan + D2H sync + duplicateWithKeys + cub radix
 //                     sort + memset + identifyTileRanges (6 launches, 1 host sync) by 1 launch.
-//   * render_fwd      one CTA per 16x16 tile: empty tiles stream zeros with 128-bit stores, active
-//                     tiles composite front-to-back.  Each output element is written exactly once
-//                     (the reference writes it twice: torch::full then renderCUDA).  No final_T /
-//                     n_contrib side buffers: backward recomputes them per active tile.
+//   * fill_zero + render_active: the dense image is streamed out as zeros with 128-bit stores (pure
+//                     HBM-write stream) and only the ~100 ACTIVE tiles are composited and overwritten.
+//                     No final_T / n_contrib side buffers: backward recomputes them per active tile.
 //   * render_bwd      CTAs loop over ACTIVE tiles only; reads dL/dimage on those tiles only;
 //                     per-(tile,Gaussian) partial sums by warp shuffles -> scratch, no atomics.
 //   * gauss_bwd       one CTA per view: fixed-order sum of the partials + EWA / projection / cov3D chain.
@@ -221,64 +220,64 @@ bin_kernel(ssb_gaussians g, ssb_cameras cams, int rcap, int n2, StateLayout L, i
 }
 
 // ------------------------------------------------------------------------------------------ render fwd
-// One CTA per tile.  Entries are staged through shared memory in chunks of 256 like the classic
-// tile rasteriser; the difference is in the traffic: one store per output element, none for side buffers.
+// The dense contract says "a freshly written [C,H,W] image", and >97 % of it is zeros.  Two kernels:
+//   fill_zero_kernel      pure streaming 128-bit stores over each view's image + inverse depth (HBM-write bound);
+//   render_active_kernel  CTAs loop over the view's ACTIVE tiles only (compact list from bin_kernel) and overwrite
+//                         them with the composited values (~3 % of the bytes are written twice).
+// The reference writes every element twice (torch::full, then renderCUDA on all tiles) plus 12 B/pixel of side
+// buffers (final_T, n_contrib, ranges sized W*H); here backward recomputes those on the active tiles instead.
+constexpr int FILL_THREADS = 256;
+
+__device__ __forceinline__ void fill_zero(float* __restrict__ p, size_t n, size_t g, size_t stride) {
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) >> 2;
+    if (head > n) head = n;
+    if (g < head) p[g] = 0.f;
+    float4* p4 = reinterpret_cast<float4*>(p + head);
+    const size_t n4 = (n - head) >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t i = g;
+    for (; i + 3 * stride < n4; i += 4 * stride) {      // 4 independent 16-B stores in flight per thread
+        p4[i] = z; p4[i + stride] = z; p4[i + 2 * stride] = z; p4[i + 3 * stride] = z;
+    }
+    for (; i < n4; i += stride) p4[i] = z;
+    const size_t tail = head + (n4 << 2) + g;
+    if (tail < n) p[tail] = 0.f;
+}
+
+__global__ void __launch_bounds__(FILL_THREADS)
+fill_zero_kernel(ssb_cameras cams, int C, float* __restrict__ out_color, const int64_t* __restrict__ color_offsets,
+                 float* __restrict__ out_invdepth, const int64_t* __restrict__ invdepth_offsets)
+{
+    const int b = blockIdx.y;
+    const int cam = b % cams.n_views;
+    const int W = cams.dims ? cams.dims[2 * cam] : cams.W0;
+    const int H = cams.dims ? cams.dims[2 * cam + 1] : cams.H0;
+    const size_t HW = (size_t)H * W;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    fill_zero(out_color + (color_offsets ? color_offsets[b] : (int64_t)b * C * (int64_t)cams.H0 * cams.W0), (size_t)C * HW, g, stride);
+    if (out_invdepth)
+        fill_zero(out_invdepth + (invdepth_offsets ? invdepth_offsets[b] : (int64_t)b * (int64_t)cams.H0 * cams.W0), HW, g, stride);
+}
+
 template <int C>
 __global__ void __launch_bounds__(TILE * TILE)
-render_fwd_kernel(ssb_gaussians g, ssb_cameras cams, StateLayout L, const char* __restrict__ state,
-                  float* __restrict__ out_color, const int64_t* __restrict__ color_offsets,
-                  float* __restrict__ out_invdepth, const int64_t* __restrict__ invdepth_offsets)
+render_active_kernel(ssb_gaussians g, ssb_cameras cams, StateLayout L, const char* __restrict__ state,
+                     float* __restrict__ out_color, const int64_t* __restrict__ color_offsets,
+                     float* __restrict__ out_invdepth, const int64_t* __restrict__ invdepth_offsets)
 {
-    const int b = blockIdx.z;
+    const int b = blockIdx.y;
     const int frame = b / cams.n_views, cam = b % cams.n_views;
     const int W = cams.dims ? cams.dims[2 * cam] : cams.W0;
     const int H = cams.dims ? cams.dims[2 * cam + 1] : cams.H0;
-    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    if ((int)blockIdx.x >= gx || (int)blockIdx.y >= gy) return;
+    const int gx = (W + TILE - 1) / TILE;
     const char* st = state + (size_t)b * L.total;
-    const uint2 range = cfield<uint2>(st, L, SSB_F_RANGES)[blockIdx.y * gx + blockIdx.x];
+    const int n_active = cfield<int>(st, L, SSB_F_HEADER)[1];
+    const uint32_t* tile_ids = cfield<uint32_t>(st, L, SSB_F_TILE_IDS);
+    const uint2* tile_ranges = cfield<uint2>(st, L, SSB_F_TILE_RANGES);
     const size_t HW = (size_t)H * W;
     float* color = out_color + (color_offsets ? color_offsets[b] : (int64_t)b * C * (int64_t)cams.H0 * cams.W0);
     float* invd = out_invdepth ? out_invdepth + (invdepth_offsets ? invdepth_offsets[b] : (int64_t)b * (int64_t)cams.H0 * cams.W0) : nullptr;
     const int tid = threadIdx.y * TILE + threadIdx.x;
-    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
-
-    if (range.x == range.y) {
-        // ---- empty tile: stream zeros.  Vector width by alignment of rows and planes.
-        const int tw = min(TILE, W - x0), th = min(TILE, H - y0);
-        const bool al4 = ((W & 3) == 0) && ((HW & 3) == 0) && tw == TILE && ((reinterpret_cast<uintptr_t>(color) & 15) == 0);
-        const bool al2 = ((W & 1) == 0) && ((HW & 1) == 0) && ((tw & 1) == 0) && ((reinterpret_cast<uintptr_t>(color) & 7) == 0);
-        if (al4) {
-            // per plane: th rows x 4 float4
-            const int per_plane = th * 4;
-            for (int i = tid; i < per_plane * C; i += TILE * TILE) {
-                const int c = i / per_plane, r = i - c * per_plane;
-                const int row = r >> 2, q = r & 3;
-                *reinterpret_cast<float4*>(color + (size_t)c * HW + (size_t)(y0 + row) * W + x0 + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else if (al2) {
-            const int hw = tw >> 1, per_plane = th * hw;
-            for (int i = tid; i < per_plane * C; i += TILE * TILE) {
-                const int c = i / per_plane, r = i - c * per_plane;
-                const int row = r / hw, q = r - row * hw;
-                *reinterpret_cast<float2*>(color + (size_t)c * HW + (size_t)(y0 + row) * W + x0 + 2 * q) = make_float2(0.f, 0.f);
-            }
-        } else {
-            const int per_plane = th * tw;
-            for (int i = tid; i < per_plane * C; i += TILE * TILE) {
-                const int c = i / per_plane, r = i - c * per_plane;
-                const int row = r / tw, q = r - row * tw;
-                color[(size_t)c * HW + (size_t)(y0 + row) * W + x0 + q] = 0.f;
-            }
-        }
-        if (invd) {
-            const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
-            if (px < W && py < H) invd[(size_t)py * W + px] = 0.f;
-        }
-        return;
-    }
-
-    // ---- active tile: front-to-back compositing (forward.cu:278-401)
     const uint32_t* point_list = cfield<uint32_t>(st, L, SSB_F_POINT_LIST);
     const float2* means2D = cfield<float2>(st, L, SSB_F_MEANS2D);
     const float4* conic_opacity = cfield<float4>(st, L, SSB_F_CONIC_OPACITY);
@@ -289,45 +288,51 @@ render_fwd_kernel(ssb_gaussians g, ssb_cameras cams, StateLayout L, const char* 
     __shared__ float4 s_co[TILE * TILE];
     __shared__ float s_invd[TILE * TILE];
 
-    const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    bool done = !inside;
-    float T = 1.0f, inv_acc = 0.0f;
-    float acc[C];
+    for (int a = blockIdx.x; a < n_active; a += gridDim.x) {
+        // ---- front-to-back compositing of one active tile (forward.cu:278-401)
+        const uint32_t tile = tile_ids[a];
+        const uint2 range = tile_ranges[a];
+        const int px = (int)(tile % gx) * TILE + threadIdx.x, py = (int)(tile / gx) * TILE + threadIdx.y;
+        const bool inside = px < W && py < H;
+        const float pxf = (float)px, pyf = (float)py;
+        bool done = !inside;
+        float T = 1.0f, inv_acc = 0.0f;
+        float acc[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) acc[c] = 0.f;
-    int todo = (int)(range.y - range.x);
-    for (uint32_t base = range.x; base < range.y; base += TILE * TILE, todo -= TILE * TILE) {
-        if (__syncthreads_count(done) == TILE * TILE) break;
-        if (base + tid < range.y) {
-            const int id = (int)point_list[base + tid];
-            s_id[tid] = id;
-            s_xy[tid] = means2D[id];
-            s_co[tid] = conic_opacity[id];
-            s_invd[tid] = __frcp_rn(depths[id]);
+        for (int c = 0; c < C; c++) acc[c] = 0.f;
+        int todo = (int)(range.y - range.x);
+        for (uint32_t base = range.x; base < range.y; base += TILE * TILE, todo -= TILE * TILE) {
+            if (__syncthreads_count(done) == TILE * TILE) break;
+            if (base + tid < range.y) {
+                const int id = (int)point_list[base + tid];
+                s_id[tid] = id;
+                s_xy[tid] = means2D[id];
+                s_co[tid] = conic_opacity[id];
+                s_invd[tid] = __frcp_rn(depths[id]);
+            }
+            __syncthreads();
+            const int n = min(TILE * TILE, todo);
+            for (int j = 0; !done && j < n; j++) {
+                const float2 xy = s_xy[j];
+                const float4 co = s_co[j];
+                float dx, dy, G, alpha;
+                if (!pair_alpha(xy.x, xy.y, co.x, co.y, co.z, co.w, pxf, pyf, dx, dy, G, alpha)) continue;
+                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                if (test_T < T_EPS) { done = true; continue; }
+                const float* f = feats + (size_t)s_id[j] * C;
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[c] = __fmaf_rn(T, __fmul_rn(alpha, __ldg(f + c)), acc[c]);
+                inv_acc = __fmaf_rn(T, __fmul_rn(alpha, s_invd[j]), inv_acc);
+                T = test_T;
+            }
         }
-        __syncthreads();
-        const int n = min(TILE * TILE, todo);
-        for (int j = 0; !done && j < n; j++) {
-            const float2 xy = s_xy[j];
-            const float4 co = s_co[j];
-            float dx, dy, G, alpha;
-            if (!pair_alpha(xy.x, xy.y, co.x, co.y, co.z, co.w, pxf, pyf, dx, dy, G, alpha)) continue;
-            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (test_T < T_EPS) { done = true; continue; }
-            const float* f = feats + (size_t)s_id[j] * C;
+        if (inside) {
+            const size_t pix = (size_t)py * W + px;
 #pragma unroll
-            for (int c = 0; c < C; c++) acc[c] = __fmaf_rn(T, __fmul_rn(alpha, __ldg(f + c)), acc[c]);
-            inv_acc = __fmaf_rn(T, __fmul_rn(alpha, s_invd[j]), inv_acc);
-            T = test_T;
+            for (int c = 0; c < C; c++) color[(size_t)c * HW + pix] = acc[c];
+            if (invd) invd[pix] = inv_acc;
         }
-    }
-    if (inside) {
-        const size_t pix = (size_t)py * W + px;
-#pragma unroll
-        for (int c = 0; c < C; c++) color[(size_t)c * HW + pix] = acc[c];
-        if (invd) invd[pix] = inv_acc;
+        __syncthreads();    // staging buffers are reused by the next tile
     }
 }
 
@@ -660,9 +665,17 @@ int ssb_rasterize_forward(int n_frames, const ssb_gaussians* g, const ssb_camera
             return ssb_set_cuda_error(cudaGetLastError());
     }
     bin_kernel<<<B, BIN_THREADS, smem, stream>>>(*g, *cams, rcap, n2, L, Wmax, Hmax, (char*)state, radii);
-    const dim3 grid((Wmax + TILE - 1) / TILE, (Hmax + TILE - 1) / TILE, B), block(TILE, TILE);
-    SSB_DISPATCH_C(g->C, render_fwd_kernel<CC><<<grid, block, 0, stream>>>(*g, *cams, L, (const char*)state, out_color,
-                                                                            color_offsets, out_invdepth, invdepth_offsets));
+    // zero fill: enough CTAs to saturate HBM writes at any batch size (148 SMs x 8), at most one 16-B store set per thread
+    int fx = (148 * 8 + B - 1) / B;
+    fx = fx < 8 ? 8 : fx;
+    fill_zero_kernel<<<dim3(fx, B), FILL_THREADS, 0, stream>>>(*cams, g->C, out_color, color_offsets, out_invdepth, invdepth_offsets);
+    if (g->P > 0) {
+        int G = (148 * 8 + B - 1) / B;
+        G = G < 4 ? 4 : (G > 256 ? 256 : G);
+        const dim3 grid(G, B), block(TILE, TILE);
+        SSB_DISPATCH_C(g->C, render_active_kernel<CC><<<grid, block, 0, stream>>>(*g, *cams, L, (const char*)state, out_color,
+                                                                                  color_offsets, out_invdepth, invdepth_offsets));
+    }
     return ssb_set_cuda_error(cudaGetLastError());
 }
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libskelsplat_b200.so")
+LIB_PATH = os.environ.get("SKELSPLAT_B200_LIB", os.path.join(_HERE, "_lib", "libskelsplat_b200.so"))   # override: tuning variants only
 
 SSB_OK = 0
 

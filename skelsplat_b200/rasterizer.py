@@ -172,14 +172,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         P = means3D.size(0)
         H, W = int(rs.image_height), int(rs.image_width)
         dev = means3D.device
+        if P == 0:   # RAST/rasterize_points.cu:88: nothing is launched, outputs are zeros
+            ctx.empty = True
+            return (torch.zeros((n_channels, H, W), dtype=torch.float32, device=dev), torch.zeros((0,), dtype=torch.int32, device=dev),
+                    torch.zeros((1, H, W), dtype=torch.float32, device=dev))
         use_sh = sh.numel() != 0
         feats = _f32c(sh if use_sh else colors_precomp).reshape(P, -1)
-        if P and feats.shape[1] != n_channels:
+        if feats.shape[1] != n_channels:
             raise RuntimeError(f"this rasteriser variant renders {n_channels} channels, got features with {feats.shape[1]}")
-        if P == 0:   # RAST/rasterize_points.cu:88: nothing is launched, outputs are zeros
-            color = torch.zeros((n_channels, H, W), dtype=torch.float32, device=dev)
-            ctx.empty = True
-            return color, torch.zeros((0,), dtype=torch.int32, device=dev), torch.zeros((1, H, W), dtype=torch.float32, device=dev)
         has_cov = cov3Ds_precomp.numel() != 0
         m3 = _f32c(means3D).unsqueeze(0)
         sc = None if has_cov else _f32c(scales).unsqueeze(0)

@@ -131,13 +131,35 @@ def make_opt_config(cfg: SceneConfig, r_capacity=256, iterations=None):
 
 
 def default_r_capacity(cfg: SceneConfig):
-    # (Gaussian,tile) pairs per view: ~10/joint at H36M/OP scale, ~25-60/joint at Panoptic scale
-    return 1024 if cfg.name == "panoptic" else 512
+    """(Gaussian,tile) pairs per view held in shared memory.  ~10/joint at H36M/OP scale, 25-60/joint at Panoptic scale.
+    Small capacities raise occupancy; frames that outgrow the capacity are detected on the device and re-run (below)."""
+    return 512 if cfg.name == "panoptic" else 256
+
+
+MAX_R_CAPACITY = 1024
+
+
+def _launch(ps: PackedSequence, oc, lr, final_loss):
+    L = _L.lib()
+    cfg = ps.cfg
+    lr_c = (C.c_double * len(lr))(*lr.tolist())
+    cams = _L.Cameras(cfg.nviews, _L.ptr(ps.viewmatrix), _L.ptr(ps.projmatrix), _L.ptr(ps.dims), _L.ptr(ps.tanfov),
+                      ps.Wmax, ps.Hmax, 0.0, 0.0, int(cfg.antialiasing))
+    F = ps.xyz.shape[0]
+    ws = torch.zeros(max(int(L.ssb_optimize_workspace_bytes(C.byref(oc), C.c_int(F))), 4) // 4, dtype=torch.int32, device=ps.xyz.device)
+    rc = L.ssb_optimize_frames(C.byref(oc), C.c_int(F), C.byref(cams), lr_c, _L.ptr(ps.xyz), _L.ptr(ps.scaling),
+                               _L.ptr(ps.rotation), _L.ptr(ps.opacity), _L.ptr(ps.roi_rect), _L.ptr(ps.roi_offset),
+                               _L.ptr(ps.roi_data), _L.ptr(final_loss), _L.ptr(ws), _L.current_stream())
+    _L.check(rc, "ssb_optimize_frames")
+    return ws[:F]
 
 
 def optimize_packed(ps: PackedSequence, iterations=None, r_capacity=None, final_loss=None, check=True):
-    """Run the fused optimiser in place on a PackedSequence.  Returns (xyz [F,J,3], final_loss [F])."""
-    L = _L.lib()
+    """Run the fused optimiser in place on a PackedSequence.  Returns (xyz [F,J,3], final_loss [F]).
+
+    check=True (default) reads the per-frame status words back (one small D2H, a host sync) and transparently
+    re-runs, from their initial state and with a doubled capacity, the frames whose (Gaussian,tile) lists outgrew
+    ``r_capacity``; check=False skips the read-back (benchmark inner loops that verify separately)."""
     cfg = ps.cfg
     if cfg.loss_function != "l2_gaussian":
         raise NotImplementedError("the fused optimiser implements the loss every shipped config uses (l2_gaussian); "
@@ -145,21 +167,30 @@ def optimize_packed(ps: PackedSequence, iterations=None, r_capacity=None, final_
     rcap = default_r_capacity(cfg) if r_capacity is None else r_capacity
     oc = make_opt_config(cfg, rcap, iterations)
     lr = xyz_lr_table(cfg, ps.spatial_lr_scale, oc.iterations)
-    lr_c = (C.c_double * len(lr))(*lr.tolist())
-    cams = _L.Cameras(cfg.nviews, _L.ptr(ps.viewmatrix), _L.ptr(ps.projmatrix), _L.ptr(ps.dims), _L.ptr(ps.tanfov),
-                      ps.Wmax, ps.Hmax, 0.0, 0.0, int(cfg.antialiasing))
     F = ps.n_frames
     if final_loss is None:
         final_loss = torch.empty(F, dtype=torch.float32, device=ps.xyz.device)
-    ws = torch.zeros(max(int(L.ssb_optimize_workspace_bytes(C.byref(oc), C.c_int(F))), 4) // 4, dtype=torch.int32, device=ps.xyz.device)
-    rc = L.ssb_optimize_frames(C.byref(oc), C.c_int(F), C.byref(cams), lr_c, _L.ptr(ps.xyz), _L.ptr(ps.scaling),
-                               _L.ptr(ps.rotation), _L.ptr(ps.opacity), _L.ptr(ps.roi_rect), _L.ptr(ps.roi_offset),
-                               _L.ptr(ps.roi_data), _L.ptr(final_loss), _L.ptr(ws), _L.current_stream())
-    _L.check(rc, "ssb_optimize_frames")
+    init = tuple(t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity)) if check else None
+    status = _launch(ps, oc, lr, final_loss)
     if check:
-        bad = int((ws[:F] != 0).sum().item())
-        if bad:
-            raise _L.SkelSplatLibraryError(f"{bad} frame(s) exceeded r_capacity={rcap} (Gaussian,tile) pairs per view")
+        bad = torch.nonzero(status != 0).flatten()
+        while bad.numel():
+            if r_capacity is not None or rcap >= MAX_R_CAPACITY:
+                raise _L.SkelSplatLibraryError(f"{bad.numel()} frame(s) exceeded r_capacity={rcap} (Gaussian,tile) pairs per view")
+            rcap *= 2
+            oc = make_opt_config(cfg, rcap, iterations)
+            sub = PackedSequence(cfg=cfg, n_frames=int(bad.numel()), xyz=init[0][bad].contiguous(), scaling=init[1][bad].contiguous(),
+                                 rotation=init[2][bad].contiguous(), opacity=init[3][bad].contiguous(), viewmatrix=ps.viewmatrix,
+                                 projmatrix=ps.projmatrix, dims=ps.dims, tanfov=ps.tanfov, roi_rect=ps.roi_rect[bad].contiguous(),
+                                 roi_offset=ps.roi_offset[bad].contiguous(), roi_data=ps.roi_data, spatial_lr_scale=ps.spatial_lr_scale,
+                                 Wmax=ps.Wmax, Hmax=ps.Hmax)
+            sub_loss = torch.empty(sub.n_frames, dtype=torch.float32, device=ps.xyz.device)
+            sub_status = _launch(sub, oc, lr, sub_loss)
+            good = sub_status == 0
+            idx = bad[good]
+            ps.xyz[idx] = sub.xyz[good]; ps.scaling[idx] = sub.scaling[good]; ps.rotation[idx] = sub.rotation[good]
+            ps.opacity[idx] = sub.opacity[good]; final_loss[idx] = sub_loss[good]
+            bad = bad[~good]
     return ps.xyz, final_loss
 
 

@@ -10,7 +10,7 @@ It needs oracle/_ref/libref_rast_*.so (built here from /root/reference by oracle
                          seeded dL (two runs: the reference's atomics make it non-reproducible, the
                          second run records its own spread)
   opt_<config>.npz       final joint positions of the restated train.py loop on the reference kernels
-                         (500 iterations) for seeded synthetic frames, plus a second run of frame 0
+                         (500 iterations) for seeded synthetic frames, plus two re-runs of every frame (the reference's own spread)
 """
 import argparse
 import os
@@ -71,15 +71,16 @@ def make_opt(cfg_name, out, n_frames=4, seed=1, iterations=500):
     cfg = configs.get_config(cfg_name)
     seq = synthetic.make_sequence(cfg, n_frames, seed=seed)
     ext = cameras_extent(seq.cameras)
-    finals, second = [], None
+    finals, reruns = [], []
     for fi, frame in enumerate(seq.frames):
         _, scal0, rot0, _ = trainer.initial_raw_state(cfg, frame.pose_3d_init[None])
         rois = heatmaps.generate_heatmap_rois(frame.pose_3d_init, frame.poses_2d, seq.cameras, scal0[0], rot0[0])
         dense = [torch.from_numpy(heatmaps.rois_to_dense(rois, v)).to(DEV) for v in range(cfg.nviews)]
         finals.append(opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend="ref", device=DEV, iterations=iterations))
-        if fi == 0:
-            second = opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend="ref", device=DEV, iterations=iterations)
-    np.savez_compressed(os.path.join(out, f"opt_{cfg_name}.npz"), ref_xyz=np.stack(finals), ref_xyz_frame0_run2=second,
+        # the reference's backward uses unordered fp32 atomics: two more runs of the SAME frame record its own spread
+        reruns.append(np.stack([opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend="ref", device=DEV, iterations=iterations)
+                                for _ in range(2)]))
+    np.savez_compressed(os.path.join(out, f"opt_{cfg_name}.npz"), ref_xyz=np.stack(finals), ref_xyz_reruns=np.stack(reruns),
                         seed=seed, n_frames=n_frames, iterations=iterations,
                         init_xyz=np.stack([f.pose_3d_init for f in seq.frames]), gt_xyz=np.stack([f.pose_3d_gt for f in seq.frames]))
     print("wrote opt", cfg_name)

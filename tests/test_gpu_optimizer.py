@@ -39,7 +39,10 @@ def test_short_run_matches_the_oracle_loop(name):
         ref = oracle_loop(cfg, seq, fi, 24)
         moved = np.linalg.norm(ref - seq.frames[fi].pose_3d_init, axis=-1).max()
         assert moved > 1.0                                    # the optimiser actually moved the joints
-        assert np.linalg.norm(mine[fi] - ref, axis=-1).max() < 0.02, name
+        # 0.1 mm: at this reduced image scale a splat covers a handful of pixels, so one pixel flipping the alpha>=1/255
+        # test between glibc's and CUDA's expf moves a gradient by ~1 %
+        assert np.linalg.norm(mine[fi] - ref, axis=-1).max() < 0.1, name
+        assert np.median(np.linalg.norm(mine[fi] - ref, axis=-1)) < 0.01, name
 
 
 @pytest.mark.parametrize("name", ["h36m", "h36m-occ", "panoptic", "occlusion-person"])
@@ -54,9 +57,38 @@ def test_full_run_against_reference_golden(name):
     ref, gt = G["ref_xyz"], G["gt_xyz"]
     assert abs(trainer.mpjpe(mine, gt) - trainer.mpjpe(ref, gt)) < 0.1                     # MPJPE within 0.1 mm
     dev = np.linalg.norm(mine - ref, axis=-1)
-    spread = float(np.linalg.norm(G["ref_xyz_frame0_run2"] - ref[0], axis=-1).max())       # the reference vs itself
-    assert dev.max() < max(0.1, 6.0 * spread), (name, dev.max(), spread)
+    spread = float(np.linalg.norm(G["ref_xyz_reruns"] - ref[:, None], axis=-1).max())      # the reference vs itself (3 runs/frame)
+    assert abs(trainer.mpjpe(mine, gt) - trainer.mpjpe(ref, gt)) < max(0.02, 0.1 * spread)
+    assert dev.max() < max(0.1, 3.0 * spread), (name, dev.max(), spread)
     assert np.median(dev) < 0.1
+
+
+@pytest.mark.parametrize("name", ["h36m", "panoptic"])
+def test_two_adam_steps_from_a_non_degenerate_state(name):
+    """Anisotropic scales and rotated quaternions make every gradient (incl. rotation, whose gradient is exactly zero in the
+    symmetric initial state) well defined; after 2 Adam steps all raw parameters must match the oracle loop."""
+    cfg = small_config(configs.get_config(name), factor=2)
+    seq = synthetic.make_sequence(cfg, 1, seed=14)
+    J = cfg.n_joints
+    rng = np.random.default_rng(5)
+    scal = (cfg.scaling + 0.8 + rng.uniform(-0.4, 0.4, (J, 3))).astype(np.float32)
+    rot = rng.normal(size=(J, 4)).astype(np.float32)
+    poses_init = np.stack([f.pose_3d_init for f in seq.frames]); poses_2d = np.stack([f.poses_2d for f in seq.frames])
+    ps = trainer.pack_sequence(cfg, seq.cameras, poses_init, poses_2d, DEV)
+    ps.scaling.copy_(torch.from_numpy(scal)[None]); ps.rotation.copy_(torch.from_numpy(rot)[None])
+    trainer.optimize_packed(ps, iterations=8)
+    fr = seq.frames[0]
+    _, scal0, rot0, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+    rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal0[0], rot0[0])
+    dense = [torch.from_numpy(heatmaps.rois_to_dense(rois, v)) for v in range(cfg.nviews)]
+    trace = []
+    ref_xyz = opipe.optimise_frame(fr, seq.cameras, cfg, cameras_extent(seq.cameras), dense, backend="oracle", device="cpu",
+                                   iterations=8, trace=trace, init_override=(scal, rot))
+    lr_xyz = cfg.position_lr_init * cameras_extent(seq.cameras)
+    assert np.abs(ps.xyz[0].cpu().numpy() - ref_xyz).max() < 0.02 * lr_xyz
+    assert np.abs(ps.scaling[0].cpu().numpy() - trace[-1]["scaling"]).max() < 0.02 * cfg.scaling_lr
+    assert np.abs(ps.rotation[0].cpu().numpy() - trace[-1]["rotation"]).max() < 0.02 * cfg.rotation_lr
+    assert np.abs(trace[-1]["rotation"] - rot).max() > 0.5 * cfg.rotation_lr       # the rotation group really stepped
 
 
 def test_full_size_properties():
