@@ -190,6 +190,25 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
                         const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
                         float* final_loss, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-frame setup on the GPU.
+ * ------------------------------------------------------------------------------------------ */
+/* Batched DLT triangulation.  Replaces triangulate_poses / triangulate_points_multi_camera (triangulation.py:122-150).
+ * P [V,3,4] fp64 projection matrices K[R|t]; poses_2d [F,V,J,2] fp64; out_xyz [F,J,3] fp64 (dehomogenised). */
+int ssb_triangulate_dlt(int n_frames, int V, int J, const double* P, const double* poses_2d, double* out_xyz, void* stream);
+
+/* Pseudo-GT heatmaps as ROI patches.  Replaces generate_heatmaps (utils/general_utils.py:175-304).  Two steps so the
+ * caller can size the packed buffer:  (1) rectangles / sigmas / peak positions / patch sizes for every (frame,view,joint);
+ * (2) after an exclusive scan of roi_size into roi_offset, fill the normalised patches.
+ * xyz [F,J,3], scaling_raw [F,J,3] (log), rotation_raw [F,J,4], poses_2d [F,V,J,2] fp32;
+ * roi_rect [F,V,J,4] int32 (x0,y0,w,h), roi_sigma [F,V,J,2] (sigma_y, sigma_x), roi_center [F,V,J,2] int32 (x,y),
+ * roi_size / roi_offset [F,V,J] int64, roi_data fp32. */
+int ssb_heatmap_roi_rects(int n_frames, int J, const ssb_cameras* cams, const float* xyz, const float* scaling_raw,
+                          const float* rotation_raw, const float* poses_2d, float scaling_modifier,
+                          int* roi_rect, float* roi_sigma, int* roi_center, int64_t* roi_size, void* stream);
+int ssb_heatmap_roi_fill(int n_frames, int J, const ssb_cameras* cams, const int* roi_rect, const float* roi_sigma,
+                         const int* roi_center, const int64_t* roi_offset, float* roi_data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

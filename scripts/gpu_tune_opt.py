@@ -24,8 +24,8 @@ print(json.dumps({"ms": min(ts), "fps": F / min(ts) * 1e3, "checksum": float(np.
 
 def main():
     from skelsplat_b200 import build
-    variants = [(256, 2), (384, 2), (512, 2), (256, 3), (256, 4)]
-    works = [("h36m", 2048, 512), ("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512), ("panoptic", 1024, 1024)]
+    variants = [(384, 2), (512, 2), (640, 1), (768, 1), (1024, 1)]
+    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 256), ("panoptic", 1024, 512)]
     out = {}
     for thr, cta in variants:
         lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
@@ -44,7 +44,7 @@ def main():
 if __name__ == "__main__":
     if "--build-only" in sys.argv:
         from skelsplat_b200 import build
-        for thr, cta in [(256, 2), (384, 2), (512, 2), (256, 3), (256, 4)]:
+        for thr, cta in [(384, 2), (512, 2), (640, 1), (768, 1), (1024, 1)]:
             build.build(force=True, defines=(f"SSB_OPT_THREADS={thr}", f"SSB_OPT_MIN_CTAS={cta}"),
                         out=os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so"))
     else:

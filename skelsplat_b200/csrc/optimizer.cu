@@ -90,6 +90,117 @@ struct SlotSplats {
     uint16_t tiles[MAXJ], offs[MAXJ];      // tiles touched, inclusive scan
 };
 
+// Per (pixel, Gaussian) backward terms (backward.cu:600-636) given alpha, G, T before the Gaussian, the pixel deltas,
+// the unscaled dL/drender of the Gaussian's own channel (gpix) and the recurrence value S.
+__device__ __forceinline__ void pair_backward(float (&acc)[NPART], const float4 A, const float4 B, float dx, float dy, float G,
+                                              float Tb, float gpix, float S, float ddelx_dx, float ddely_dy) {
+    const float dL_dalpha = (gpix - S) * Tb;
+    const float dL_dG = A.z * dL_dalpha;
+    const float gdx = G * dx, gdy = G * dy;
+    const float dG_ddelx = -gdx * B.x - gdy * B.y;
+    const float dG_ddely = -gdy * B.z - gdx * B.y;
+    acc[0] += dL_dG * dG_ddelx * ddelx_dx;
+    acc[1] += dL_dG * dG_ddely * ddely_dy;
+    acc[2] += -0.5f * gdx * dx * dL_dG;
+    acc[3] += -0.5f * gdx * dy * dL_dG;
+    acc[4] += -0.5f * gdy * dy * dL_dG;
+    acc[5] += G * dL_dalpha;
+}
+
+// One reduction per (tile, entry): 8 values (6 used) in 9 shuffles; 6 lanes store the totals.
+__device__ __forceinline__ void reduce_store_partial(const float (&acc)[NPART], float* __restrict__ dst, int lane) {
+    float r8[8] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], 0.f, 0.f};
+    const float tot = warp_multi_reduce<8>(r8, lane);
+    const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
+    if ((lane & 3) == 0 && idx < NPART) dst[idx] = tot;
+}
+
+// A tile whose list has exactly N <= FAST Gaussians: everything per-entry lives in registers, loops are fully unrolled.
+// The GT patch addressing is hoisted out of the pass loop: per entry a base offset, a row stride for two rows, and the
+// range of passes whose row falls inside the patch (columns are pass-invariant for a lane).
+template <int N>
+__device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
+                                          const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
+                                          int lx, int ly0, int W, int H, float ddelx_dx, float ddely_dy, bool want_loss,
+                                          float* __restrict__ part_out, int lane, float& my_lsum, int& my_cnt)
+{
+    int gid[N], goff[N], gw2[N];
+    unsigned grange[N];
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        const int g = list[u];
+        gid[u] = g;
+        const int4 roi = roi_v[g];
+        const int rx = lx - roi.x, ry0 = ly0 - roi.y;
+        int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                 // first pass with ry0 + 2*pass >= 0
+        int phi = (roi.w - ry0 + 1) >> 1;                          // first pass with ry0 + 2*pass >= h
+        phi = phi > TILE / 2 ? TILE / 2 : phi;
+        if (!((unsigned)rx < (unsigned)roi.z) || phi <= plo) { plo = 0; phi = 0; }
+        grange[u] = (unsigned)plo | ((unsigned)(phi - plo) << 8);
+        goff[u] = roi_rel_v[g] + ry0 * roi.z + rx;
+        gw2[u] = 2 * roi.z;
+    }
+    float accv[N][NPART];
+#pragma unroll
+    for (int u = 0; u < N; u++)
+#pragma unroll
+        for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
+    float lsum = 0.f; int cnt = 0;
+    if (lx < W) {
+        for (int pass = 0; pass < TILE / 2; pass++) {
+            const int py = ly0 + 2 * pass;
+            if (py >= H) break;
+            const float pxf = (float)lx, pyf = (float)py;
+            float al[N], Gv[N], Tb[N];
+            unsigned ok = 0u;
+            float T = 1.0f;
+            bool done = false;
+            // forward replay (forward.cu:330-386): alpha, G and the transmittance before each accumulated Gaussian
+#pragma unroll
+            for (int u = 0; u < N; u++) {
+                al[u] = 0.f; Gv[u] = 0.f; Tb[u] = 0.f;
+                if (!done) {
+                    const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
+                    float dx, dy, G, alpha;
+                    if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) {
+                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        if (test_T < T_EPS) done = true;
+                        else { al[u] = alpha; Gv[u] = G; Tb[u] = T; ok |= 1u << u; T = test_T; }
+                    }
+                }
+            }
+            if (ok == 0u) continue;
+            // GT values of the contributing Gaussians' channels: all loads issued before any is consumed
+            float gtv[N];
+#pragma unroll
+            for (int u = 0; u < N; u++) {
+                gtv[u] = 0.f;
+                if (((ok >> u) & 1u) && (unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8))
+                    gtv[u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
+            }
+            // backward replay (backward.cu:536-636) with the one-hot scalar recurrence
+            float S = 0.f, last_alpha = 0.f, last_g = 0.f;
+#pragma unroll
+            for (int u = N - 1; u >= 0; u--) {
+                if ((ok >> u) & 1u) {
+                    const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
+                    const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
+                    const float err = al[u] * Tb[u] - gtv[u];      // rendered value of channel g minus GT
+                    const float gpix = 2.f * err;                    // unscaled dL/drender (x 1/N later)
+                    S = last_alpha * last_g + (1.f - last_alpha) * S;
+                    last_g = gpix; last_alpha = al[u];
+                    cnt += (gtv[u] > 0.f) ? 0 : 1;                   // mask pixel outside {gt > 0}
+                    if (want_loss) lsum += (gtv[u] > 0.f) ? (err * err - gtv[u] * gtv[u]) : (err * err);
+                    pair_backward(accv[u], A, B, dx, dy, Gv[u], Tb[u], gpix, S, ddelx_dx, ddely_dy);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < N; u++) reduce_store_partial(accv[u], part_out + (size_t)u * NPART, lane);
+    my_lsum += lsum; my_cnt += cnt;
+}
+
 template <int SLOTS>
 __global__ void __launch_bounds__(OPT_THREADS, SSB_OPT_MIN_CTAS)
 optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ StepTable tab)
@@ -105,7 +216,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ float s_accg[MAXV][MAXJ * 3];                                                  // accumulated_grads[V,J,3]
     __shared__ float s_act_scale[MAXJ * 3], s_act_q[MAXJ * 4], s_act_qn[MAXJ], s_act_op[MAXJ], s_cov3d[MAXJ * 6];
     __shared__ float s_view[MAXV][16], s_proj[MAXV][16];
-    __shared__ int s_W[MAXV], s_H[MAXV];
+    __shared__ int s_W[MAXV], s_H[MAXV], s_slot_view[MAX_SLOTS];
+    __shared__ float s_halfW[MAXV], s_halfH[MAXV];
     __shared__ float s_tfx[MAXV], s_tfy[MAXV], s_fx[MAXV], s_fy[MAXV];
     __shared__ int4 s_roi[MAXV][MAXJ];          // x0, y0, w, h
     __shared__ int s_roi_rel[MAXV][MAXJ];        // float offset relative to the frame's first patch
@@ -138,6 +250,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         const int W = p.cams.dims ? p.cams.dims[2 * tid] : p.cams.W0, H = p.cams.dims ? p.cams.dims[2 * tid + 1] : p.cams.H0;
         const float tfx = p.cams.tanfov ? p.cams.tanfov[2 * tid] : p.cams.tanfovx0, tfy = p.cams.tanfov ? p.cams.tanfov[2 * tid + 1] : p.cams.tanfovy0;
         s_W[tid] = W; s_H[tid] = H; s_tfx[tid] = tfx; s_tfy[tid] = tfy;
+        s_halfW[tid] = 0.5f * W; s_halfH[tid] = 0.5f * H;
         s_fy[tid] = __fdiv_rn((float)H, __fmul_rn(2.0f, tfy));
         s_fx[tid] = __fdiv_rn((float)W, __fmul_rn(2.0f, tfx));
         s_ngt[tid] = 0; s_sgt2[tid] = 0.f;
@@ -188,7 +301,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 #pragma unroll
             for (int k = 0; k < 6; k++) s_cov3d[6 * j + k] = cov[k];
         }
-        if (tid < SLOTS) { s_cnt[tid] = 0; }
+        if (tid < SLOTS) { s_cnt[tid] = 0; s_slot_view[tid] = (step * acc + tid) % V; }
         if (tid < SLOTS * OPT_WARPS) (&s_lsum[0][0])[tid] = 0.f;
         __syncthreads();
         if (tid < SLOTS * J) {
@@ -272,6 +385,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         }
         if (warp < SLOTS) {      // warp k: ordered compaction of the tile runs of slot k
             const int k = warp, R = s_R[k];
+            const uint32_t gxk = (uint32_t)((s_W[s_slot_view[k]] + TILE - 1) / TILE);
             const uint64_t* K = SSB_KEYS(k);
             int nact = 0;
             for (int base = 0; base < R; base += 32) {
@@ -281,7 +395,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, start);
                 if (start) {
                     const int a = nact + __popc(m & ((1u << lane) - 1u));
-                    d_tile[(size_t)k * RCAP + a] = (uint16_t)tile;
+                    d_tile[(size_t)k * RCAP + a] = (uint16_t)(((tile / gxk) << 8) | (tile % gxk));
                     d_start[(size_t)k * RCAP + a] = (uint16_t)i;
                 }
                 nact += __popc(m);
@@ -299,116 +413,29 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             int lcnt[SLOTS];
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) { lsum[k] = 0.f; lcnt[k] = 0; }
+            const bool want_loss = (step == p.n_steps - 1);
+            const float* roi_base = p.roi_data + s_roi_base;
             for (int item = warp; item < total; item += OPT_WARPS) {
                 int k = 0, a = item;
 #pragma unroll
                 for (int kk = 0; kk < SLOTS - 1; kk++) { if (k == kk && a >= s_nact[kk]) { a -= s_nact[kk]; k = kk + 1; } }
-                const int v = (step * acc + k) % V;
+                const int v = s_slot_view[k];
                 const int W = s_W[v], H = s_H[v];
-                const int gx = (W + TILE - 1) / TILE;
-                const int tile = d_tile[(size_t)k * RCAP + a];
+                const int tile = d_tile[(size_t)k * RCAP + a];                 // packed (ty << 8) | tx
                 const int e0 = d_start[(size_t)k * RCAP + a];
                 const int e1 = (a + 1 < s_nact[k]) ? (int)d_start[(size_t)k * RCAP + a + 1] : s_R[k];
                 const int n = e1 - e0;
                 const SlotSplats& sp = s_sp[k];
                 const uint16_t* list = d_list + (size_t)k * RCAP + e0;
-                const int tx0 = (tile % gx) * TILE, ty0 = (tile / gx) * TILE;
-                const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-                const float* roi_base = p.roi_data + s_roi_base;
+                const float ddelx_dx = s_halfW[v], ddely_dy = s_halfH[v];
                 float my_lsum = 0.f; int my_cnt = 0;
-                const int lx = tx0 + (lane & 15), ly0 = ty0 + (lane >> 4);
-
-                // per (pixel, Gaussian) backward terms given alpha, G, T(before), the deltas and the unscaled dL/drender
-#define SSB_PAIR_BWD(ACC, A, B, dx, dy, G, alpha, Tb, gpix, S)                                              \
-                {                                                                                           \
-                    const float dL_dalpha = ((gpix) - (S)) * (Tb);                                          \
-                    const float dL_dG = (A).z * dL_dalpha;                                                  \
-                    const float gdx = (G) * (dx), gdy = (G) * (dy);                                         \
-                    const float dG_ddelx = -gdx * (B).x - gdy * (B).y;                                      \
-                    const float dG_ddely = -gdy * (B).z - gdx * (B).y;                                      \
-                    ACC[0] += dL_dG * dG_ddelx * ddelx_dx;                                                  \
-                    ACC[1] += dL_dG * dG_ddely * ddely_dy;                                                  \
-                    ACC[2] += -0.5f * gdx * (dx) * dL_dG;                                                   \
-                    ACC[3] += -0.5f * gdx * (dy) * dL_dG;                                                   \
-                    ACC[4] += -0.5f * gdy * (dy) * dL_dG;                                                   \
-                    ACC[5] += (G) * dL_dalpha;                                                              \
-                }
-                // GT value of channel g at pixel (px,py): ROI patch lookup (0 outside the patch)
-#define SSB_GT(gt, g, px, py)                                                                               \
-                {                                                                                           \
-                    const int4 roi = s_roi[v][g];                                                           \
-                    const int rx = (px) - roi.x, ry = (py) - roi.y;                                         \
-                    gt = 0.f;                                                                               \
-                    if ((unsigned)rx < (unsigned)roi.z && (unsigned)ry < (unsigned)roi.w)                   \
-                        gt = __ldg(roi_base + s_roi_rel[v][g] + ry * roi.z + rx);                           \
-                }
-
-                if (n <= FAST) {
-                    // ---------- fast path: the whole tile list lives in registers (alpha, G, T cached from the forward replay)
-                    int gid[FAST];
-#pragma unroll
-                    for (int u = 0; u < FAST; u++) gid[u] = (u < n) ? (int)list[u] : 0;
-                    float accv[FAST][NPART];
-#pragma unroll
-                    for (int u = 0; u < FAST; u++)
-#pragma unroll
-                        for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
-                    for (int pass = 0; pass < TILE / 2; pass++) {
-                        const int px = lx, py = ly0 + 2 * pass;
-                        if (!(px < W && py < H)) continue;          // no warp-collective operation inside the pass loop
-                        const float pxf = (float)px, pyf = (float)py;
-                        float al[FAST], Gv[FAST], Tb[FAST];
-                        unsigned ok = 0u;
-                        float T = 1.0f;
-                        bool done = false;
-#pragma unroll
-                        for (int u = 0; u < FAST; u++) {
-                            if (u < n && !done) {
-                                const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
-                                float dx, dy, G, alpha;
-                                if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) {
-                                    const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                                    if (test_T < T_EPS) done = true;
-                                    else { al[u] = alpha; Gv[u] = G; Tb[u] = T; ok |= 1u << u; T = test_T; }
-                                }
-                            }
-                        }
-                        // all GT loads of this pixel are issued before any is consumed (independent L2 hits in flight)
-                        float gtv[FAST];
-#pragma unroll
-                        for (int u = 0; u < FAST; u++) {
-                            gtv[u] = 0.f;
-                            if (ok & (1u << u)) { SSB_GT(gtv[u], gid[u], px, py); }
-                        }
-                        float S = 0.f, last_alpha = 0.f, last_g = 0.f;
-#pragma unroll
-                        for (int u = FAST - 1; u >= 0; u--) {
-                            if (ok & (1u << u)) {
-                                const int g = gid[u];
-                                const float4 A = sp.geoA[g], B = sp.geoB[g];
-                                const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
-                                const float c = al[u] * Tb[u];               // rendered value of channel g at this pixel
-                                const float gt = gtv[u];
-                                const float err = c - gt;
-                                const float gpix = 2.f * err;                // unscaled dL/drender (x 1/N later)
-                                S = last_alpha * last_g + (1.f - last_alpha) * S;
-                                last_g = gpix; last_alpha = al[u];
-                                if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
-                                SSB_PAIR_BWD(accv[u], A, B, dx, dy, Gv[u], al[u], Tb[u], gpix, S);
-                            }
-                        }
-                    }
-                    // one reduction per (tile, entry): 8 values (6 used) in 9 shuffles
-#pragma unroll
-                    for (int u = 0; u < FAST; u++) {
-                        if (u < n) {     // warp-uniform
-                            float r8[8] = {accv[u][0], accv[u][1], accv[u][2], accv[u][3], accv[u][4], accv[u][5], 0.f, 0.f};
-                            const float tot = warp_multi_reduce<8>(r8, lane);
-                            const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
-                            if ((lane & 3) == 0 && idx < NPART) d_part[((size_t)k * RCAP + e0 + u) * NPART + idx] = tot;
-                        }
-                    }
-                } else {
+                const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
+                float* part_out = d_part + ((size_t)k * RCAP + e0) * NPART;
+                if (n == 1) tile_fast<1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
+                else if (n == 2) tile_fast<2>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
+                else if (n == 3) tile_fast<3>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
+                else if (n == 4) tile_fast<4>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
+                else {
                     // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
                     for (int c0 = 0; c0 < n; c0 += FAST) {
                         float accv[FAST][NPART];
@@ -418,7 +445,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                             for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
                         for (int pass = 0; pass < TILE / 2; pass++) {
                             const int px = lx, py = ly0 + 2 * pass;
-                            if (!(px < W && py < H)) continue;
+                            if (!(px < W && py < H)) continue;          // no warp-collective operation inside the pass loop
                             const float pxf = (float)px, pyf = (float)py;
                             // forward replay: final transmittance and last contributor (forward.cu:330-386)
                             float T = 1.0f;
@@ -441,10 +468,12 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                 float dx, dy, G, alpha;
                                 if (!pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) continue;
                                 T = T / (1.f - alpha);
-                                const float c = alpha * T;
-                                float gt;
-                                SSB_GT(gt, g, px, py);
-                                const float err = c - gt;
+                                const int4 roi = s_roi[v][g];
+                                const int rx = px - roi.x, ry = py - roi.y;
+                                float gt = 0.f;
+                                if ((unsigned)rx < (unsigned)roi.z && (unsigned)ry < (unsigned)roi.w)
+                                    gt = __ldg(roi_base + s_roi_rel[v][g] + ry * roi.z + rx);
+                                const float err = alpha * T - gt;
                                 const float gpix = 2.f * err;
                                 S = last_alpha * last_g + (1.f - last_alpha) * S;
                                 last_g = gpix; last_alpha = alpha;
@@ -452,7 +481,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                 if (u >= 0 && u < FAST) {
                                     if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
                                     float w[NPART] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                                    SSB_PAIR_BWD(w, A, B, dx, dy, G, alpha, T, gpix, S);
+                                    pair_backward(w, A, B, dx, dy, G, T, gpix, S, ddelx_dx, ddely_dy);
 #pragma unroll
                                     for (int uu = 0; uu < FAST; uu++)
                                         if (u == uu) {
@@ -463,18 +492,10 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < FAST; u++) {
-                            if (c0 + u < n) {     // warp-uniform
-                                float r8[8] = {accv[u][0], accv[u][1], accv[u][2], accv[u][3], accv[u][4], accv[u][5], 0.f, 0.f};
-                                const float tot = warp_multi_reduce<8>(r8, lane);
-                                const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
-                                if ((lane & 3) == 0 && idx < NPART) d_part[((size_t)k * RCAP + e0 + c0 + u) * NPART + idx] = tot;
-                            }
-                        }
+                        for (int u = 0; u < FAST; u++)
+                            if (c0 + u < n) reduce_store_partial(accv[u], part_out + (size_t)(c0 + u) * NPART, lane);   // warp-uniform
                     }
                 }
-#undef SSB_PAIR_BWD
-#undef SSB_GT
 #pragma unroll
                 for (int kk = 0; kk < SLOTS; kk++) if (k == kk) { lsum[kk] += my_lsum; lcnt[kk] += my_cnt; }
             }

@@ -1,0 +1,245 @@
+// Per-frame setup on the GPU (SURVEY.md section 8 "next" rows f-3 and f-1), sm_100a.
+//
+//  * dlt_kernel           batched DLT triangulation: the producer of the initial guess
+//                         (reference: triangulation.py:122-150, one numpy SVD per joint on the CPU).
+//  * roi_rect_kernel /    pseudo-ground-truth heatmaps as ROI patches, batched over frames x views x joints
+//    roi_fill_kernel      (reference: utils/general_utils.py:175-304, V*J cupy gaussian_filter calls on megapixel
+//                         images with .item() syncs per frame).
+// Both are embarrassingly parallel and tiny per item; they exist so that initial guess -> heatmaps -> optimisation
+// runs as one GPU pipeline with no per-frame host work.
+#include "api_internal.h"
+
+namespace ssb {
+
+// ------------------------------------------------------------------------------------------ DLT
+constexpr int DLT_MAXV = 16;
+
+// Smallest-eigenvalue eigenvector of a symmetric 4x4 matrix by cyclic Jacobi rotations (fp64).
+__device__ void smallest_eigvec4(double M[4][4], double out[4]) {
+    double Vm[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < 4; i++) {
+            diag += M[i][i] * M[i][i];
+            for (int j = i + 1; j < 4; j++) off += M[i][j] * M[i][j];
+        }
+        if (off <= 1e-60 * diag || off == 0.0) break;
+        for (int pi = 0; pi < 3; pi++)
+            for (int qi = pi + 1; qi < 4; qi++) {
+                const double apq = M[pi][qi];
+                if (apq == 0.0) continue;
+                const double theta = (M[qi][qi] - M[pi][pi]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 4; k++) {            // M <- M J
+                    const double mkp = M[k][pi], mkq = M[k][qi];
+                    M[k][pi] = c * mkp - sn * mkq;
+                    M[k][qi] = sn * mkp + c * mkq;
+                }
+                for (int k = 0; k < 4; k++) {            // M <- J^T M
+                    const double mpk = M[pi][k], mqk = M[qi][k];
+                    M[pi][k] = c * mpk - sn * mqk;
+                    M[qi][k] = sn * mpk + c * mqk;
+                }
+                for (int k = 0; k < 4; k++) {
+                    const double vkp = Vm[k][pi], vkq = Vm[k][qi];
+                    Vm[k][pi] = c * vkp - sn * vkq;
+                    Vm[k][qi] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0;
+    for (int i = 1; i < 4; i++) if (M[i][i] < M[best][best]) best = i;
+    for (int k = 0; k < 4; k++) out[k] = Vm[k][best];
+}
+
+// One thread per (frame, joint).  P: [V,3,4] fp64 projection matrices K[R|t]; poses_2d: [F,V,J,2] fp64.
+__global__ void dlt_kernel(int F, int V, int J, const double* __restrict__ P, const double* __restrict__ poses_2d,
+                           double* __restrict__ out /* [F,J,3] */)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * J) return;
+    const int f = i / J, j = i % J;
+    double M[4][4];
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) M[a][b] = 0.0;
+    for (int v = 0; v < V; v++) {
+        const double* Pv = P + (size_t)v * 12;
+        const double x = poses_2d[(((size_t)f * V + v) * J + j) * 2], y = poses_2d[(((size_t)f * V + v) * J + j) * 2 + 1];
+        double r0[4], r1[4];
+        for (int k = 0; k < 4; k++) { r0[k] = x * Pv[8 + k] - Pv[k]; r1[k] = y * Pv[8 + k] - Pv[4 + k]; }   // triangulation.py:128-129
+        for (int a = 0; a < 4; a++) for (int b = a; b < 4; b++) M[a][b] += r0[a] * r0[b] + r1[a] * r1[b];
+    }
+    for (int a = 0; a < 4; a++) for (int b = 0; b < a; b++) M[a][b] = M[b][a];
+    double x4[4];
+    smallest_eigvec4(M, x4);
+    out[(size_t)i * 3] = x4[0] / x4[3]; out[(size_t)i * 3 + 1] = x4[1] / x4[3]; out[(size_t)i * 3 + 2] = x4[2] / x4[3];
+}
+
+// ------------------------------------------------------------------------------------------ heatmap ROIs
+// sigma of the (view, joint) heatmap from the INITIAL Gaussian, restating utils/general_utils.py:199-265 in fp32:
+// T = R_w2c @ J_rows (not the rasteriser's EWA form), cov = T^T Sigma^T T, +0.3 on the diagonal,
+// lambda = mid +- sqrt(max(0.1, mid^2 - det)); sigma_y = sqrt(lambda1) (axis 0), sigma_x = sqrt(lambda2) (axis 1).
+struct RoiParams {
+    int F, V, J;
+    const float* xyz; const float* scaling_raw; const float* rotation_raw;   // [F,J,3] [F,J,3] [F,J,4]
+    const float* poses_2d;                                                    // [F,V,J,2]
+    ssb_cameras cams;
+    float scaling_modifier;
+};
+
+__device__ __forceinline__ int gauss_radius(float sigma) { return (int)(4.0f * sigma + 0.5f); }   // scipy: int(truncate*sd + 0.5)
+
+__global__ void roi_rect_kernel(RoiParams p, int* __restrict__ roi_rect, float* __restrict__ roi_sigma, int* __restrict__ roi_center,
+                                long long* __restrict__ roi_size)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.F * p.V * p.J) return;
+    const int j = i % p.J, v = (i / p.J) % p.V, f = i / (p.J * p.V);
+    const int W = p.cams.dims ? p.cams.dims[2 * v] : p.cams.W0, H = p.cams.dims ? p.cams.dims[2 * v + 1] : p.cams.H0;
+    const float tfx = p.cams.tanfov ? p.cams.tanfov[2 * v] : p.cams.tanfovx0, tfy = p.cams.tanfov ? p.cams.tanfov[2 * v + 1] : p.cams.tanfovy0;
+    const float* vm = p.cams.viewmatrix + 16 * v;            // stored transposed: W2C(r,c) = vm[4*c + r]
+    const size_t gj = (size_t)f * p.J + j;
+    const float mx = p.xyz[3 * gj], my = p.xyz[3 * gj + 1], mz = p.xyz[3 * gj + 2];
+    // Sigma = (R S)(R S)^T with the NORMALISED quaternion (build_rotation normalises, general_utils.py:87-108)
+    float q0 = p.rotation_raw[4 * gj], q1 = p.rotation_raw[4 * gj + 1], q2 = p.rotation_raw[4 * gj + 2], q3 = p.rotation_raw[4 * gj + 3];
+    const float qn = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 /= qn; q1 /= qn; q2 /= qn; q3 /= qn;
+    const float r = q0, x = q1, y = q2, z = q3;
+    const float R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)},
+                           {2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)},
+                           {2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)}};
+    float s[3];
+    for (int k = 0; k < 3; k++) s[k] = expf(p.scaling_raw[3 * gj + k]) * p.scaling_modifier;
+    float Sg[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+        float acc = 0.f;
+        for (int k = 0; k < 3; k++) acc += (R[a][k] * s[k]) * (R[b][k] * s[k]);
+        Sg[a][b] = acc;
+    }
+    float t[3];
+    for (int a = 0; a < 3; a++) t[a] = vm[a] * mx + vm[4 + a] * my + vm[8 + a] * mz + vm[12 + a];
+    const float fx = (float)W / (2.0f * tfx), fy = (float)H / (2.0f * tfy);
+    const float limx = 1.3f * tfx, limy = 1.3f * tfy;
+    t[0] = fminf(limx, fmaxf(-limx, t[0] / t[2])) * t[2];
+    t[1] = fminf(limy, fmaxf(-limy, t[1] / t[2])) * t[2];
+    const float Jr[2][3] = {{fx / t[2], 0.f, -(fx * t[0]) / (t[2] * t[2])}, {0.f, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}};
+    // T = Wm @ Jm with Wm = W2C[:3,:3] and Jm rows (Jr[0], Jr[1], 0): T[a][b] = Wm[a][0]*Jr[0][b] + Wm[a][1]*Jr[1][b]
+    float T[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) T[a][b] = vm[4 * 0 + a] * Jr[0][b] + vm[4 * 1 + a] * Jr[1][b];
+    // cov = T^T Sigma^T T, entries (0,0), (0,1), (1,1)
+    float c00 = 0.f, c01 = 0.f, c11 = 0.f;
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+        c00 += T[a][0] * Sg[b][a] * T[b][0];
+        c01 += T[a][0] * Sg[b][a] * T[b][1];
+        c11 += T[a][1] * Sg[b][a] * T[b][1];
+    }
+    const float cx = c00 + 0.3f, cz = c11 + 0.3f;
+    const float det = cx * cz - c01 * c01;
+    const float mid = 0.5f * (cx + cz);
+    const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float s1 = sqrtf(mid + root), s2 = sqrtf(mid - root);
+    // peak at (clamp(int(v)), clamp(int(u))): .long() truncates toward zero (general_utils.py:275-278)
+    const float u = p.poses_2d[2 * (size_t)i], vv = p.poses_2d[2 * (size_t)i + 1];
+    const int xc = min(max((int)u, 0), W - 1), yc = min(max((int)vv, 0), H - 1);
+    const int ry = gauss_radius(s1), rx = gauss_radius(s2);
+    const int x0 = max(0, xc - rx), x1 = min(W - 1, xc + rx), y0 = max(0, yc - ry), y1 = min(H - 1, yc + ry);
+    roi_rect[4 * (size_t)i] = x0; roi_rect[4 * (size_t)i + 1] = y0; roi_rect[4 * (size_t)i + 2] = x1 - x0 + 1; roi_rect[4 * (size_t)i + 3] = y1 - y0 + 1;
+    roi_sigma[2 * (size_t)i] = s1; roi_sigma[2 * (size_t)i + 1] = s2;
+    roi_center[2 * (size_t)i] = xc; roi_center[2 * (size_t)i + 1] = yc;
+    roi_size[i] = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
+}
+
+// Response at index idx of scipy's correlate1d(mode='reflect') with the truncated Gaussian (sigma, radius) to a unit delta
+// at pos on an axis of length n:  sum_k w[k] * [reflect(idx + k - radius) == pos].
+__device__ double reflect_response(int idx, int pos, int n, double sigma, int radius, double wsum_inv) {
+    double acc = 0.0;
+    const double c = -0.5 / (sigma * sigma);
+    for (int k = 0; k <= 2 * radius; k++) {
+        int src = idx + k - radius;
+        if (src < 0) src = -src - 1;
+        if (src >= n) src = 2 * n - 1 - src;
+        if (src == pos) { const double d = (double)(k - radius); acc += exp(c * d * d) * wsum_inv; }
+    }
+    return acc;
+}
+
+// One CTA per (frame, view, joint) patch: separable filter response, fp32 storage after pass 1 (as scipy does),
+// then per-channel min-max normalisation (min == 0: the patch never covers the whole image) with the +1e-8.
+__global__ void __launch_bounds__(128)
+roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __restrict__ roi_sigma, const int* __restrict__ roi_center,
+                const long long* __restrict__ roi_offset, ssb_cameras cams, int V, int J, float* __restrict__ roi_data)
+{
+    const int i = blockIdx.x;
+    if (i >= n_patches) return;
+    const int v = (i / J) % V;
+    const int W = cams.dims ? cams.dims[2 * v] : cams.W0, H = cams.dims ? cams.dims[2 * v + 1] : cams.H0;
+    const int x0 = roi_rect[4 * (size_t)i], y0 = roi_rect[4 * (size_t)i + 1], w = roi_rect[4 * (size_t)i + 2], h = roi_rect[4 * (size_t)i + 3];
+    const double s1 = (double)roi_sigma[2 * (size_t)i], s2 = (double)roi_sigma[2 * (size_t)i + 1];
+    const int xc = roi_center[2 * (size_t)i], yc = roi_center[2 * (size_t)i + 1];
+    const int ry = (int)(4.0 * s1 + 0.5), rx = (int)(4.0 * s2 + 0.5);
+    __shared__ float s_col[256];
+    __shared__ double s_row[256];
+    __shared__ float s_max;
+    if (w > 256 || h > 256) return;            // sigma > 31 px: not a SkelSplat regime (host validates)
+    double wy = 0.0, wx = 0.0;
+    for (int k = -ry; k <= ry; k++) wy += exp(-0.5 / (s1 * s1) * (double)(k * k));
+    for (int k = -rx; k <= rx; k++) wx += exp(-0.5 / (s2 * s2) * (double)(k * k));
+    for (int t = threadIdx.x; t < h; t += blockDim.x) s_col[t] = (float)(255.0 * reflect_response(y0 + t, yc, H, s1, ry, 1.0 / wy));
+    for (int t = threadIdx.x; t < w; t += blockDim.x) s_row[t] = reflect_response(x0 + t, xc, W, s2, rx, 1.0 / wx);
+    __syncthreads();
+    if (threadIdx.x == 0) {      // max of the rounded products == rounded product of the maxima (all factors >= 0, rounding is monotonic)
+        float mc = 0.f; double mr = 0.0;
+        for (int a = 0; a < h; a++) mc = fmaxf(mc, s_col[a]);
+        for (int b = 0; b < w; b++) mr = fmax(mr, s_row[b]);
+        s_max = (float)((double)mc * mr);
+    }
+    __syncthreads();
+    float* dst = roi_data + roi_offset[i];
+    const float denom = s_max + 1e-8f;
+    for (int t = threadIdx.x; t < w * h; t += blockDim.x) {
+        const int a = t / w, b = t - a * w;
+        dst[t] = (float)((double)s_col[a] * s_row[b]) / denom;
+    }
+}
+
+}  // namespace ssb
+
+using namespace ssb;
+
+extern "C" {
+
+int ssb_triangulate_dlt(int n_frames, int V, int J, const double* P, const double* poses_2d, double* out_xyz, void* stream_) {
+    if (n_frames < 0 || V < 2 || V > DLT_MAXV || J <= 0) return SSB_ERR_INVALID;
+    if (n_frames == 0) return SSB_OK;
+    if (!P || !poses_2d || !out_xyz) return SSB_ERR_INVALID;
+    const int n = n_frames * J;
+    dlt_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(n_frames, V, J, P, poses_2d, out_xyz);
+    return ssb_set_cuda_error(cudaGetLastError());
+}
+
+int ssb_heatmap_roi_rects(int n_frames, int J, const ssb_cameras* cams, const float* xyz, const float* scaling_raw,
+                          const float* rotation_raw, const float* poses_2d, float scaling_modifier,
+                          int* roi_rect, float* roi_sigma, int* roi_center, int64_t* roi_size, void* stream_) {
+    if (!cams || n_frames < 0 || J <= 0 || cams->n_views <= 0) return SSB_ERR_INVALID;
+    if (n_frames == 0) return SSB_OK;
+    if (!xyz || !scaling_raw || !rotation_raw || !poses_2d || !roi_rect || !roi_sigma || !roi_center || !roi_size) return SSB_ERR_INVALID;
+    RoiParams p;
+    p.F = n_frames; p.V = cams->n_views; p.J = J; p.xyz = xyz; p.scaling_raw = scaling_raw; p.rotation_raw = rotation_raw;
+    p.poses_2d = poses_2d; p.cams = *cams; p.scaling_modifier = scaling_modifier;
+    const int n = n_frames * cams->n_views * J;
+    roi_rect_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(p, roi_rect, roi_sigma, roi_center, (long long*)roi_size);
+    return ssb_set_cuda_error(cudaGetLastError());
+}
+
+int ssb_heatmap_roi_fill(int n_frames, int J, const ssb_cameras* cams, const int* roi_rect, const float* roi_sigma,
+                         const int* roi_center, const int64_t* roi_offset, float* roi_data, void* stream_) {
+    if (!cams || n_frames < 0 || J <= 0 || cams->n_views <= 0) return SSB_ERR_INVALID;
+    if (n_frames == 0) return SSB_OK;
+    if (!roi_rect || !roi_sigma || !roi_center || !roi_offset || !roi_data) return SSB_ERR_INVALID;
+    const int n = n_frames * cams->n_views * J;
+    roi_fill_kernel<<<n, 128, 0, (cudaStream_t)stream_>>>(n, roi_rect, roi_sigma, roi_center, (const long long*)roi_offset, *cams,
+                                                          cams->n_views, J, roi_data);
+    return ssb_set_cuda_error(cudaGetLastError());
+}
+
+}  // extern "C"

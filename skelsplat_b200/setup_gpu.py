@@ -1,0 +1,73 @@
+"""Per-frame setup on the GPU: batched DLT initial guess and GT heatmap ROIs.
+
+Host counterparts (numpy, used by the CPU tests and as the readable specification): ``triangulation.triangulate_poses``
+and ``heatmaps.generate_heatmap_rois``.  With these two kernels a whole sequence goes detections -> initial guess ->
+heatmap ROIs -> fused optimisation without any per-frame host work (``pack_sequence_gpu``).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _L
+from .cameras import cameras_extent
+from .configs import SceneConfig
+from .trainer import PackedSequence, camera_tensors, initial_raw_state
+
+
+def triangulate_dlt(P_list, poses_2d, device="cuda"):
+    """[F,J,3] float64 tensor from V projection matrices K[R|t] and detections [F,V,J,2] (triangulation.py:122-150)."""
+    L = _L.lib()
+    P = torch.as_tensor(np.asarray(P_list, np.float64)).to(device).contiguous()
+    d = torch.as_tensor(np.asarray(poses_2d, np.float64)).to(device).contiguous()
+    F, V, J = d.shape[0], d.shape[1], d.shape[2]
+    out = torch.empty((F, J, 3), dtype=torch.float64, device=device)
+    _L.check(L.ssb_triangulate_dlt(C.c_int(F), C.c_int(V), C.c_int(J), _L.ptr(P), _L.ptr(d), _L.ptr(out), _L.current_stream()),
+             "ssb_triangulate_dlt")
+    return out
+
+
+def generate_heatmap_rois_gpu(cfg: SceneConfig, vm, pm, dims, tanfov, Wmax, Hmax, xyz, scaling, rotation, poses_2d):
+    """Device tensors in, device tensors out: (roi_rect [F,V,J,4] int32, roi_offset [F,V,J] int64, roi_data [total] fp32)."""
+    L = _L.lib()
+    F, J, V = xyz.shape[0], cfg.n_joints, cfg.nviews
+    dev = xyz.device
+    cams = _L.Cameras(V, _L.ptr(vm), _L.ptr(pm), _L.ptr(dims), _L.ptr(tanfov), Wmax, Hmax, 0.0, 0.0, 0)
+    rect = torch.empty((F, V, J, 4), dtype=torch.int32, device=dev)
+    sigma = torch.empty((F, V, J, 2), dtype=torch.float32, device=dev)
+    center = torch.empty((F, V, J, 2), dtype=torch.int32, device=dev)
+    size = torch.empty((F, V, J), dtype=torch.int64, device=dev)
+    p2d = poses_2d.to(torch.float32).contiguous()
+    _L.check(L.ssb_heatmap_roi_rects(C.c_int(F), C.c_int(J), C.byref(cams), _L.ptr(xyz), _L.ptr(scaling), _L.ptr(rotation), _L.ptr(p2d),
+                                     C.c_float(1.0), _L.ptr(rect), _L.ptr(sigma), _L.ptr(center), _L.ptr(size), _L.current_stream()),
+             "ssb_heatmap_roi_rects")
+    csum = torch.cumsum(size.reshape(-1), 0)
+    offset = (csum - size.reshape(-1)).reshape(F, V, J).contiguous()
+    total = int(csum[-1].item())                       # the one host sync of the setup: sizes the packed buffer
+    if int(rect[..., 2:].max().item()) > 256:
+        raise _L.SkelSplatLibraryError("heatmap patch wider than 256 px (sigma > 31 px): outside the supported regime")
+    data = torch.empty(total, dtype=torch.float32, device=dev)
+    _L.check(L.ssb_heatmap_roi_fill(C.c_int(F), C.c_int(J), C.byref(cams), _L.ptr(rect), _L.ptr(sigma), _L.ptr(center), _L.ptr(offset),
+                                    _L.ptr(data), _L.current_stream()), "ssb_heatmap_roi_fill")
+    return rect, offset, data
+
+
+def pack_sequence_gpu(cfg: SceneConfig, cams, poses_2d, poses_init=None, device="cuda") -> PackedSequence:
+    """detections [F,V,J,2] (+ optional initial poses) -> PackedSequence, entirely on the GPU.
+    Without ``poses_init`` the initial guess is the DLT triangulation of the detections (BASELINE config 1)."""
+    poses_2d = np.asarray(poses_2d)
+    F = poses_2d.shape[0]
+    d2 = torch.as_tensor(poses_2d).to(device)
+    if poses_init is None:
+        init = triangulate_dlt([c.P3x4() for c in cams], d2, device).to(torch.float32)
+    else:
+        init = torch.as_tensor(np.asarray(poses_init, np.float32)).to(device)
+    _, scal, rot, opa = initial_raw_state(cfg, np.zeros((F, cfg.n_joints, 3), np.float32))
+    scaling, rotation, opacity = (torch.from_numpy(a).to(device) for a in (scal, rot, opa))
+    vm, pm, dims, tanfov = camera_tensors(cams, device)
+    Wmax, Hmax = max(c.image_width for c in cams), max(c.image_height for c in cams)
+    xyz = init.contiguous()
+    rect, offset, data = generate_heatmap_rois_gpu(cfg, vm, pm, dims, tanfov, Wmax, Hmax, xyz, scaling, rotation, d2)
+    return PackedSequence(cfg=cfg, n_frames=F, xyz=xyz.clone(), scaling=scaling, rotation=rotation, opacity=opacity, viewmatrix=vm,
+                          projmatrix=pm, dims=dims, tanfov=tanfov, roi_rect=rect, roi_offset=offset, roi_data=data,
+                          spatial_lr_scale=cameras_extent(cams), Wmax=Wmax, Hmax=Hmax)

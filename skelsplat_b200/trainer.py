@@ -133,7 +133,7 @@ def make_opt_config(cfg: SceneConfig, r_capacity=256, iterations=None):
 def default_r_capacity(cfg: SceneConfig):
     """(Gaussian,tile) pairs per view held in shared memory.  ~10/joint at H36M/OP scale, 25-60/joint at Panoptic scale.
     Small capacities raise occupancy; frames that outgrow the capacity are detected on the device and re-run (below)."""
-    return 512 if cfg.name == "panoptic" else 256
+    return {"panoptic": 1024, "occlusion-person": 512}.get(cfg.name, 256)
 
 
 MAX_R_CAPACITY = 1024

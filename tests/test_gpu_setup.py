@@ -1,0 +1,63 @@
+"""GPU setup kernels (rows f-3, f-1) against their host (numpy) specifications, which the CPU suite pins against the
+reference procedures (tests/test_host_logic.py)."""
+import numpy as np
+import pytest
+import torch
+
+from skelsplat_b200 import configs, heatmaps, setup_gpu, synthetic, trainer, triangulation
+from tests.util import small_config
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("name", ["h36m", "panoptic", "occlusion-person-8v"])
+def test_dlt_matches_numpy_svd(name):
+    cfg = configs.get_config(name)
+    seq = synthetic.make_sequence(cfg, 16, seed=3)
+    P_list = [c.P3x4() for c in seq.cameras]
+    det = np.stack([f.poses_2d for f in seq.frames])
+    got = setup_gpu.triangulate_dlt(P_list, det, DEV).cpu().numpy()
+    want = np.stack([triangulation.triangulate_poses(P_list, d) for d in det])
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-6            # millimetres, fp64 on both sides
+    assert np.abs(want - np.stack([f.pose_3d_init for f in seq.frames])).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", ["h36m", "panoptic", "occlusion-person"])
+def test_heatmap_rois_match_the_host_generator(name):
+    cfg = configs.get_config(name)
+    seq = synthetic.make_sequence(cfg, 3, seed=7)
+    seq.frames[0].poses_2d[0, 0] = [2.3, 1.1]           # corner: reflect + clamp
+    seq.frames[1].poses_2d[1, 2] = [1e5, -40.0]         # outside: clamped to the border
+    poses_init = np.stack([f.pose_3d_init for f in seq.frames]); poses_2d = np.stack([f.poses_2d for f in seq.frames])
+    host = trainer.pack_host(cfg, seq.cameras, poses_init, poses_2d)
+    ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, poses_2d, poses_init, DEV)
+    rect = ps.roi_rect.cpu().numpy(); off = ps.roi_offset.cpu().numpy(); data = ps.roi_data.cpu().numpy()
+    same = (rect == host["roi_rect"]).all(-1)
+    assert same.mean() > 0.97                           # a sigma one ulp across a half-integer moves a window edge by 1 px
+    F, V, J = same.shape
+    checked = 0
+    for f in range(F):
+        for v in range(V):
+            for j in range(J):
+                if not same[f, v, j]:
+                    continue
+                w, h = rect[f, v, j, 2], rect[f, v, j, 3]
+                a = data[off[f, v, j]:off[f, v, j] + w * h]
+                b = host["roi_data"][host["roi_offset"][f, v, j]:host["roi_offset"][f, v, j] + w * h]
+                assert np.abs(a - b).max() < 2e-6
+                checked += 1
+    assert checked > 0.9 * F * V * J
+    assert abs(data.max() - 1.0) < 1e-6 and data.min() >= 0.0
+
+
+def test_whole_gpu_pipeline_detections_to_poses():
+    """detections -> DLT -> ROIs -> fused optimiser, all on the GPU, equals the host-prepared run (non-chaotic config)."""
+    cfg = configs.OCCLUSION_PERSON
+    seq = synthetic.make_sequence(cfg, 4, seed=9)
+    poses_2d = np.stack([f.poses_2d for f in seq.frames])
+    ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, poses_2d, None, DEV)          # initial guess from the GPU DLT
+    xyz, _ = trainer.optimize_packed(ps)
+    ref = trainer.optimize_sequence(seq, DEV)
+    assert np.linalg.norm(xyz.cpu().numpy() - ref, axis=-1).max() < 0.05
