@@ -131,20 +131,20 @@ def run_ours(args):
         if world > 1:
             dist.all_gather_into_tensor(gathered, ps.xyz)
 
-    host_out = torch.empty((F, cfg.n_joints, 3), dtype=torch.float32).pin_memory()
+    # e2e: the public streaming API -- every step copies that step's inputs from pinned host memory and reads the poses back;
+    # the copy of step i+1 overlaps the optimisation of step i (double-buffered)
+    so = trainer.StreamingOptimizer(cfg, seq.cameras, F, int(pinned["roi_data"].numel()), dev)
+    tickets = []
 
     def step_e2e():
-        # host buffers -> device (initial state + GT ROIs), optimise, final poses -> host
-        for k, dst in (("xyz", ps.xyz), ("scaling", ps.scaling), ("rotation", ps.rotation), ("opacity", ps.opacity),
-                       ("roi_rect", ps.roi_rect), ("roi_offset", ps.roi_offset), ("roi_data", ps.roi_data)):
-            dst.copy_(pinned[k], non_blocking=True)
-        trainer.optimize_packed(ps, check=False)
+        tickets.append(so.submit(pinned))
         launches[0] += 1
+        if len(tickets) >= 2:
+            so.result(tickets[-2])                      # poses of the previous batch are on the host before the next submit
         if world > 1:
-            dist.all_gather_into_tensor(gathered, ps.xyz)
-        host_out.copy_(ps.xyz, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, so.slots[tickets[-1] % 2]["ps"].xyz)
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, streams=()):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -157,8 +157,12 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = launches[0]
         e0.record()
+        for st in streams:                                   # side streams start after e0 ...
+            st.wait_stream(torch.cuda.current_stream())
         for _ in range(steps):
             fn()
+        for st in streams:                                   # ... and e1 is recorded after everything they did
+            torch.cuda.current_stream().wait_stream(st)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -178,14 +182,15 @@ def run_ours(args):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(); trainer.optimize_packed(ps, check=False); k1.record(); torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, streams=(so.copy_stream, so.compute_stream))
+    so.result(tickets[-1])
     final = ps.xyz.cpu().numpy()
 
     total_frames = world * F
     value = total_frames * args.steps / (ms / 1e3)
     e2e_value = total_frames * args.steps / (ms_e2e / 1e3)
     h2d = sum(int(v.numel() * v.element_size()) for v in pinned.values())
-    d2h = int(host_out.numel() * host_out.element_size())
+    d2h = int(F * cfg.n_joints * 3 * 4 + F * 4)          # final poses + per-frame status words
 
     if rank != 0:
         if world > 1:
@@ -210,6 +215,7 @@ def run_ours(args):
                         "the HBM-roofline op is the dense rasteriser in m2_rasterizer_dense"}
     m2 = bench_dense_rasterizer(torch, R, cfg, seq, dev, hbm_peak) if world == 1 else None
     cpu = cpu_baseline(cfg, seq) if world == 1 else None
+    setup = bench_setup(torch, cfg, seq, dev) if world == 1 else None
     from skelsplat_b200.trainer import mpjpe
     line = {
         "metric": "optimised_frames_per_sec", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -219,8 +225,8 @@ def run_ours(args):
                    "loss": "l2_gaussian + 1e-5 limb consistency", "parallelism": f"frame-sharded x{world}" + (", NCCL all_gather of final poses" if world > 1 else ""),
                    "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "includes": "pinned-host -> device copy of initial poses/params + GT heatmap ROIs, fused optimiser, device -> host copy of final poses"},
-        "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "cpu_baseline": cpu,
+                "ms_per_step": round(ms_e2e / args.steps, 3), "includes": "trainer.StreamingOptimizer: per step pinned-host -> device copy of initial poses/params + GT heatmap ROIs, fused optimiser, device -> host copy of final poses + status; copies of step i+1 overlap the kernel of step i"},
+        "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "setup_gpu": setup, "cpu_baseline": cpu,
         "accuracy": {"mpjpe_init_mm": round(mpjpe(host["xyz"], gt), 3), "mpjpe_final_mm": round(mpjpe(final, gt), 3)},
     }
     print(json.dumps(line), flush=True)
@@ -228,7 +234,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_dense_rasterizer(torch, R, cfg, seq, dev, hbm_peak, frames=8, reps=5):
+def bench_dense_rasterizer(torch, R, cfg, seq, dev, hbm_peak, frames=16, reps=5):
     """M2: batched dense-contract rasteriser fwd+bwd views/s against the HBM roof (R1)."""
     from skelsplat_b200 import trainer
     J = cfg.n_joints
@@ -267,6 +273,38 @@ def bench_dense_rasterizer(torch, R, cfg, seq, dev, hbm_peak, frames=8, reps=5):
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
                          "algorithmic_bytes_per_view": round(bytes_view), "traffic": None},
             "l2": f"outputs {B * bytes_view / 1e6:.0f} MB per launch > 126 MB L2 (no flush)", "kernels": "bin_kernel, render_fwd_kernel<17>, render_bwd_kernel<17>, gauss_bwd_kernel<17>"}
+
+
+def bench_setup(torch, cfg, seq, dev, F=2048):
+    """Rows f-3 / f-1: batched DLT initial guess and GT heatmap ROI generation on the GPU, with the host (numpy) versions beside them."""
+    from skelsplat_b200 import setup_gpu, trainer, heatmaps
+    from skelsplat_b200.triangulation import triangulate_poses
+    n0 = len(seq.frames)
+    poses_2d = np.concatenate([np.stack([f.poses_2d for f in seq.frames])] * ((F + n0 - 1) // n0))[:F]
+    P_list = [c.P3x4() for c in seq.cameras]
+    d2 = torch.as_tensor(poses_2d).to(dev)
+
+    def gpu_time(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / 1e3)
+        return float(np.median(ts))
+    t_dlt = gpu_time(lambda: setup_gpu.triangulate_dlt(P_list, d2, dev))
+    init = setup_gpu.triangulate_dlt(P_list, d2, dev).to(torch.float32)
+    t_roi = gpu_time(lambda: setup_gpu.pack_sequence_gpu(cfg, seq.cameras, d2, init, dev))
+    t0 = time.perf_counter()
+    for f in seq.frames[:8]:
+        triangulate_poses(P_list, f.poses_2d)
+    cpu_dlt = 8 / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    trainer.pack_host(cfg, seq.cameras, np.stack([f.pose_3d_init for f in seq.frames[:4]]), np.stack([f.poses_2d for f in seq.frames[:4]]))
+    cpu_roi = 4 / (time.perf_counter() - t0)
+    return {"frames": F, "gpu_dlt_frames_per_s": round(F / t_dlt, 1), "gpu_heatmap_roi_frames_per_s": round(F / t_roi, 1),
+            "host_numpy_dlt_frames_per_s": round(cpu_dlt, 1), "host_numpy_heatmap_roi_frames_per_s": round(cpu_roi, 2),
+            "note": "per-frame setup (SURVEY 8 rows f-3, f-1); heatmap figure includes buffer allocation and its one host sync"}
 
 
 # ----------------------------------------------------------------------------------------- CPU baseline

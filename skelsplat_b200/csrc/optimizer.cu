@@ -88,6 +88,7 @@ struct SlotSplats {
     uint32_t depth_bits[MAXJ];
     uint16_t rx0[MAXJ], ry0[MAXJ], rx1[MAXJ], ry1[MAXJ];
     uint16_t tiles[MAXJ], offs[MAXJ];      // tiles touched, inclusive scan
+    uint8_t rank[MAXJ], of_rank[MAXJ];     // depth rank of each Gaussian ((depth bits, id) order) and its inverse
 };
 
 // Per (pixel, Gaussian) backward terms (backward.cu:600-636) given alpha, G, T before the Gaussian, the pixel deltas,
@@ -151,6 +152,14 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
             const int py = ly0 + 2 * pass;
             if (py >= H) break;
             const float pxf = (float)lx, pyf = (float)py;
+            // GT values of the listed Gaussians' channels at this pixel: issued first, consumed only in the backward replay,
+            // so the L2 latency hides behind the forward math (a pixel outside a patch reads nothing and gets 0)
+            float gtv[N];
+#pragma unroll
+            for (int u = 0; u < N; u++) {
+                gtv[u] = 0.f;
+                if ((unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8)) gtv[u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
+            }
             float al[N], Gv[N], Tb[N];
             unsigned ok = 0u;
             float T = 1.0f;
@@ -170,14 +179,6 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
                 }
             }
             if (ok == 0u) continue;
-            // GT values of the contributing Gaussians' channels: all loads issued before any is consumed
-            float gtv[N];
-#pragma unroll
-            for (int u = 0; u < N; u++) {
-                gtv[u] = 0.f;
-                if (((ok >> u) & 1u) && (unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8))
-                    gtv[u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
-            }
             // backward replay (backward.cu:536-636) with the one-hot scalar recurrence
             float S = 0.f, last_alpha = 0.f, last_g = 0.f;
 #pragma unroll
@@ -229,15 +230,14 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ float s_lsum[SLOTS][OPT_WARPS];
     __shared__ int s_status;
     extern __shared__ __align__(16) unsigned char dsm[];
-    // dynamic, per slot: partial f32[RCAP*NPART] (24 B/entry) whose storage is first used by the sort's keys u64[RCAP]
-    // + payloads u32[RCAP] (dead once the tile lists exist) | list u16 | inv_pos u16 | tile u16 | start u16  => 32 B/entry
+    // dynamic, per slot: partial f32[RCAP*NPART] (24 B/entry) whose storage is first used by the sort's 32-bit words
+    // (dead once the tile lists exist) | list u16 | inv_pos u16 | tile u16 | start u16  => 32 B/entry
     float* d_part = reinterpret_cast<float*>(dsm);
     uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)SLOTS * RCAP * NPART);
     uint16_t* d_inv = d_list + (size_t)SLOTS * RCAP;
     uint16_t* d_tile = d_inv + (size_t)SLOTS * RCAP;
     uint16_t* d_start = d_tile + (size_t)SLOTS * RCAP;
-#define SSB_KEYS(k) (reinterpret_cast<uint64_t*>(d_part + (size_t)(k) * RCAP * NPART))
-#define SSB_VALS(k) (reinterpret_cast<uint32_t*>(SSB_KEYS(k) + RCAP))
+#define SSB_KEYS32(k) (reinterpret_cast<uint32_t*>(d_part + (size_t)(k) * RCAP * NPART))
 
     // ---------------- load the frame ----------------
     for (int i = tid; i < J * 3; i += OPT_THREADS) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
@@ -327,16 +327,24 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             s_R[tid] = (int)a;
         }
         __syncthreads();
-        int nsort = 32;
+        int nsort = 32, lgsort = 5;
         {
             int Rmax = 0;
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) Rmax = max(Rmax, s_R[k]);
-            while (nsort < Rmax) nsort <<= 1;       // RCAP is a power of two >= Rmax
+            while (nsort < Rmax) { nsort <<= 1; lgsort++; }       // RCAP is a power of two >= Rmax
         }
-        for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
-            const int k = i / nsort, e = i - k * nsort;
-            SSB_KEYS(k)[e] = ~0ull; SSB_VALS(k)[e] = 0xFFFFFFFFu;
+        // 32-bit sort words: tile (17 bits) | depth rank of the Gaussian (5) | emission index (10).  (tile, rank) is unique per
+        // entry, so sorting the words reproduces the reference's stable (tile | depth bits) order; the emission index rides along.
+        for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) SSB_KEYS32(i >> lgsort)[i & (nsort - 1)] = 0xFFFFFFFFu;
+        if (tid < SLOTS * J) {      // depth rank: position of (depth bits, id) among the slot's Gaussians
+            const int k = tid / J, j = tid % J;
+            SlotSplats& sp = s_sp[k];
+            const uint32_t dj = sp.depth_bits[j];
+            int r = 0;
+            for (int o = 0; o < J; o++) { const uint32_t d = sp.depth_bits[o]; r += (d < dj || (d == dj && o < j)) ? 1 : 0; }
+            sp.rank[j] = (uint8_t)r;
+            sp.of_rank[r] = (uint8_t)j;
         }
         __syncthreads();
         if (tid < SLOTS * J) {
@@ -346,12 +354,10 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const int v = (step * acc + k) % V;
                 const uint32_t gx = (uint32_t)((s_W[v] + TILE - 1) / TILE);
                 uint32_t off = (j == 0) ? 0u : sp.offs[j - 1];
+                const uint32_t low = ((uint32_t)sp.rank[j] << 10);
                 for (uint32_t y = sp.ry0[j]; y < sp.ry1[j]; y++)
                     for (uint32_t x = sp.rx0[j]; x < sp.rx1[j]; x++) {
-                        if (off < (uint32_t)s_R[k]) {
-                            SSB_KEYS(k)[off] = ((uint64_t)(y * gx + x) << 32) | sp.depth_bits[j];
-                            SSB_VALS(k)[off] = (off << 10) | (uint32_t)j;
-                        }
+                        if (off < (uint32_t)s_R[k]) SSB_KEYS32(k)[off] = ((y * gx + x) << 15) | low | off;
                         off++;
                     }
             }
@@ -360,38 +366,34 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         // bitonic sort of all slots at once (independent sub-arrays of length nsort)
         for (int kk = 2; kk <= nsort; kk <<= 1) {
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
-                    const int k = i / nsort, e = i - k * nsort;
-                    const int exj = e ^ jj;
-                    if (exj > e) {
-                        uint64_t* K = SSB_KEYS(k);
-                        uint32_t* Vv = SSB_VALS(k);
-                        const uint64_t ka = K[e], kb = K[exj];
-                        const uint32_t va = Vv[e], vb = Vv[exj];
-                        const bool a_gt_b = (ka > kb) || (ka == kb && va > vb);
-                        if (a_gt_b == ((e & kk) == 0)) { K[e] = kb; K[exj] = ka; Vv[e] = vb; Vv[exj] = va; }
-                    }
+                for (int i = tid; i < SLOTS * (nsort >> 1); i += OPT_THREADS) {
+                    // i enumerates the compare-exchange pairs: insert a 0 bit at position log2(jj)
+                    const int k = i >> (lgsort - 1), q = i & ((nsort >> 1) - 1);
+                    const int e = ((q & ~(jj - 1)) << 1) | (q & (jj - 1));
+                    uint32_t* K = SSB_KEYS32(k);
+                    const uint32_t ka = K[e], kb = K[e | jj];
+                    if ((ka > kb) == ((e & kk) == 0)) { K[e] = kb; K[e | jj] = ka; }
                 }
                 __syncthreads();
             }
         }
         for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
-            const int k = i / nsort, e = i - k * nsort;
+            const int k = i >> lgsort, e = i & (nsort - 1);
             if (e < s_R[k]) {
-                const uint32_t val = SSB_VALS(k)[e];
-                d_list[(size_t)k * RCAP + e] = (uint16_t)(val & 1023u);
-                d_inv[(size_t)k * RCAP + (val >> 10)] = (uint16_t)e;
+                const uint32_t key = SSB_KEYS32(k)[e];
+                d_list[(size_t)k * RCAP + e] = (uint16_t)s_sp[k].of_rank[(key >> 10) & 31u];
+                d_inv[(size_t)k * RCAP + (key & 1023u)] = (uint16_t)e;
             }
         }
         if (warp < SLOTS) {      // warp k: ordered compaction of the tile runs of slot k
             const int k = warp, R = s_R[k];
             const uint32_t gxk = (uint32_t)((s_W[s_slot_view[k]] + TILE - 1) / TILE);
-            const uint64_t* K = SSB_KEYS(k);
+            const uint32_t* K = SSB_KEYS32(k);
             int nact = 0;
             for (int base = 0; base < R; base += 32) {
                 const int i = base + lane;
                 bool start = false; uint32_t tile = 0;
-                if (i < R) { tile = (uint32_t)(K[i] >> 32); start = (i == 0) || ((uint32_t)(K[i - 1] >> 32) != tile); }
+                if (i < R) { tile = K[i] >> 15; start = (i == 0) || ((K[i - 1] >> 15) != tile); }
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, start);
                 if (start) {
                     const int a = nact + __popc(m & ((1u << lane) - 1u));

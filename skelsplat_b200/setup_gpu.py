@@ -19,7 +19,7 @@ def triangulate_dlt(P_list, poses_2d, device="cuda"):
     """[F,J,3] float64 tensor from V projection matrices K[R|t] and detections [F,V,J,2] (triangulation.py:122-150)."""
     L = _L.lib()
     P = torch.as_tensor(np.asarray(P_list, np.float64)).to(device).contiguous()
-    d = torch.as_tensor(np.asarray(poses_2d, np.float64)).to(device).contiguous()
+    d = (poses_2d if torch.is_tensor(poses_2d) else torch.as_tensor(np.asarray(poses_2d))).to(device=device, dtype=torch.float64).contiguous()
     F, V, J = d.shape[0], d.shape[1], d.shape[2]
     out = torch.empty((F, J, 3), dtype=torch.float64, device=device)
     _L.check(L.ssb_triangulate_dlt(C.c_int(F), C.c_int(V), C.c_int(J), _L.ptr(P), _L.ptr(d), _L.ptr(out), _L.current_stream()),

@@ -206,3 +206,85 @@ def optimize_sequence(seq, device="cuda", iterations=None, r_capacity=None):
 def mpjpe(pred, gt):
     """eval.py:122-123: mean over joints (and frames) of ||pred - gt||_2, millimetres."""
     return float(np.linalg.norm(np.asarray(pred, np.float64) - np.asarray(gt, np.float64), axis=-1).mean())
+
+
+class StreamingOptimizer:
+    """End-to-end pipeline for sequences that live in HOST memory: batch i+1's host->device copy (initial state + GT ROIs,
+    from pinned buffers) overlaps batch i's optimisation on a second CUDA stream; final poses and the per-frame status words
+    come back device->host per batch.  Double-buffered: at most two batches are resident.
+
+        so = StreamingOptimizer(cfg, cams, frames_per_batch, roi_floats_per_batch)
+        t0 = so.submit(host_batch0); t1 = so.submit(host_batch1)      # dicts of pinned tensors as trainer.pack_host() lays them out
+        xyz0 = so.result(t0)                                           # blocks on batch 0 only
+    """
+
+    def __init__(self, cfg: SceneConfig, cams, frames_per_batch, roi_floats, device="cuda", iterations=None, r_capacity=None):
+        self.cfg, self.cams, self.F, self.device = cfg, cams, frames_per_batch, device
+        self.iterations, self.r_capacity = iterations, r_capacity
+        J, V = cfg.n_joints, cfg.nviews
+        vm, pm, dims, tanfov = camera_tensors(cams, device)
+        ext = cameras_extent(cams)
+        Wmax, Hmax = max(c.image_width for c in cams), max(c.image_height for c in cams)
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)
+        self.slots = []
+        for _ in range(2):
+            ps = PackedSequence(cfg=cfg, n_frames=frames_per_batch, xyz=mk((frames_per_batch, J, 3), torch.float32),
+                                scaling=mk((frames_per_batch, J, 3), torch.float32), rotation=mk((frames_per_batch, J, 4), torch.float32),
+                                opacity=mk((frames_per_batch, J), torch.float32), viewmatrix=vm, projmatrix=pm, dims=dims, tanfov=tanfov,
+                                roi_rect=mk((frames_per_batch, V, J, 4), torch.int32), roi_offset=mk((frames_per_batch, V, J), torch.int64),
+                                roi_data=mk((roi_floats,), torch.float32), spatial_lr_scale=ext, Wmax=Wmax, Hmax=Hmax)
+            self.slots.append(dict(ps=ps, out=torch.empty((frames_per_batch, J, 3), dtype=torch.float32).pin_memory(),
+                                   status=torch.empty((frames_per_batch,), dtype=torch.int32).pin_memory(),
+                                   loss=torch.empty(frames_per_batch, dtype=torch.float32, device=device),
+                                   copied=torch.cuda.Event(), done=torch.cuda.Event(), host=None, busy=False))
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.compute_stream = torch.cuda.Stream(device=device)
+        self.n_submitted = 0
+        self.launches = 0
+
+    def submit(self, host):
+        i = self.n_submitted
+        sl = self.slots[i % 2]
+        if sl["busy"]:
+            sl["done"].synchronize()            # the buffer pair of batch i-2 must have been consumed by its kernel and copies
+        ps = sl["ps"]
+        n_roi = host["roi_data"].numel()
+        if n_roi > ps.roi_data.numel() or host["xyz"].shape[0] != self.F:
+            raise ValueError("batch does not fit the streaming buffers")
+        with torch.cuda.stream(self.copy_stream):
+            for k, dst in (("xyz", ps.xyz), ("scaling", ps.scaling), ("rotation", ps.rotation), ("opacity", ps.opacity),
+                           ("roi_rect", ps.roi_rect), ("roi_offset", ps.roi_offset)):
+                dst.copy_(host[k], non_blocking=True)
+            ps.roi_data[:n_roi].copy_(host["roi_data"], non_blocking=True)
+            sl["copied"].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(sl["copied"])
+            rcap = default_r_capacity(self.cfg) if self.r_capacity is None else self.r_capacity
+            oc = make_opt_config(self.cfg, rcap, self.iterations)
+            lr = xyz_lr_table(self.cfg, ps.spatial_lr_scale, oc.iterations)
+            status = _launch(ps, oc, lr, sl["loss"])
+            self.launches += 1
+            sl["out"].copy_(ps.xyz, non_blocking=True)
+            sl["status"].copy_(status, non_blocking=True)
+            sl["done"].record(self.compute_stream)
+        sl["host"], sl["busy"] = host, True
+        self.n_submitted += 1
+        return i
+
+    def result(self, ticket):
+        sl = self.slots[ticket % 2]
+        sl["done"].synchronize()
+        if int(sl["status"].max()) != 0:
+            # rare: some frames outgrew r_capacity -> exact synchronous re-run of the batch with the retrying path
+            ps = sl["ps"]
+            with torch.cuda.stream(self.compute_stream):
+                for k, dst in (("xyz", ps.xyz), ("scaling", ps.scaling), ("rotation", ps.rotation), ("opacity", ps.opacity)):
+                    dst.copy_(sl["host"][k], non_blocking=True)
+                optimize_packed(ps, self.iterations, None)
+                sl["out"].copy_(ps.xyz)
+            self.compute_stream.synchronize()
+        return sl["out"].numpy().copy()
+
+    def synchronize(self):
+        self.copy_stream.synchronize()
+        self.compute_stream.synchronize()
