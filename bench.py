@@ -382,7 +382,7 @@ def run_reference(args):
               "forward.cu/backward.cu/rasterizer_impl.cu for sm_100a) on the GPU + the reference's torch ops (clamp, l2_gaussian, autograd, Adam) "
               "in the restated train.py loop; per-frame setup (heatmaps) excluded, as in our arm") if use_ref else \
              f"{len(secs)} frames x {iters} iterations on the CPU oracle port (oracle/_ref not loadable), extrapolated to 500"
-    line = {"impl": "reference", "metric": "optimised_frames_per_sec", "value": round(value, 4), "unit": "frames/s", "n_gpus": 1,
+    line = {"impl": "reference", "metric": "optimised_frames_per_sec", "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus, "ranks_used": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(per_frame * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": 1, "iterations": cfg.iterations},

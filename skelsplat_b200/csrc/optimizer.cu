@@ -41,6 +41,7 @@ constexpr int MAX_SLOTS = 4;
 constexpr int MAX_STEPS = 256;
 constexpr int FAST = 4;            // tile-list entries whose gradient sums are held in registers at once
 constexpr int NPART = 6;           // dmean2D.x, dmean2D.y, dconic.x, dconic.y, dconic.w, dopacity
+constexpr int PSTRIDE = 8;         // per-entry partial record: NPART gradient sums + loss term + mask count (as float)
 
 struct StepTable {                 // host-computed in fp64, rounded to fp32 like torch's scalar->tensor ops
     float neg_step_xyz[MAX_STEPS];
@@ -93,7 +94,7 @@ struct SlotSplats {
 
 // Per (pixel, Gaussian) backward terms (backward.cu:600-636) given alpha, G, T before the Gaussian, the pixel deltas,
 // the unscaled dL/drender of the Gaussian's own channel (gpix) and the recurrence value S.
-__device__ __forceinline__ void pair_backward(float (&acc)[NPART], const float4 A, const float4 B, float dx, float dy, float G,
+__device__ __forceinline__ void pair_backward(float (&acc)[PSTRIDE], const float4 A, const float4 B, float dx, float dy, float G,
                                               float Tb, float gpix, float S, float ddelx_dx, float ddely_dy) {
     const float dL_dalpha = (gpix - S) * Tb;
     const float dL_dG = A.z * dL_dalpha;
@@ -108,12 +109,12 @@ __device__ __forceinline__ void pair_backward(float (&acc)[NPART], const float4 
     acc[5] += G * dL_dalpha;
 }
 
-// One reduction per (tile, entry): 8 values (6 used) in 9 shuffles; 6 lanes store the totals.
-__device__ __forceinline__ void reduce_store_partial(const float (&acc)[NPART], float* __restrict__ dst, int lane) {
-    float r8[8] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], 0.f, 0.f};
+// One reduction per (tile, entry): 8 values (6 gradient sums, loss term, mask count) in 9 shuffles; 8 lanes store the totals.
+__device__ __forceinline__ void reduce_store_partial(const float (&acc)[PSTRIDE], float* __restrict__ dst, int lane) {
+    float r8[8] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]};
     const float tot = warp_multi_reduce<8>(r8, lane);
     const int idx = ((lane & 16) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 4) ? 1 : 0);
-    if ((lane & 3) == 0 && idx < NPART) dst[idx] = tot;
+    if ((lane & 3) == 0) dst[idx] = tot;
 }
 
 // A tile whose list has exactly N <= FAST Gaussians: everything per-entry lives in registers, loops are fully unrolled.
@@ -123,7 +124,7 @@ template <int N>
 __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
                                           const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
                                           int lx, int ly0, int W, int H, float ddelx_dx, float ddely_dy, bool want_loss,
-                                          float* __restrict__ part_out, int lane, float& my_lsum, int& my_cnt)
+                                          float* __restrict__ part_out, int lane)
 {
     int gid[N], goff[N], gw2[N];
     unsigned grange[N];
@@ -141,12 +142,11 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
         goff[u] = roi_rel_v[g] + ry0 * roi.z + rx;
         gw2[u] = 2 * roi.z;
     }
-    float accv[N][NPART];
+    float accv[N][PSTRIDE];
 #pragma unroll
     for (int u = 0; u < N; u++)
 #pragma unroll
-        for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
-    float lsum = 0.f; int cnt = 0;
+        for (int q = 0; q < PSTRIDE; q++) accv[u][q] = 0.f;
     if (lx < W) {
         for (int pass = 0; pass < TILE / 2; pass++) {
             const int py = ly0 + 2 * pass;
@@ -190,16 +190,15 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
                     const float gpix = 2.f * err;                    // unscaled dL/drender (x 1/N later)
                     S = last_alpha * last_g + (1.f - last_alpha) * S;
                     last_g = gpix; last_alpha = al[u];
-                    cnt += (gtv[u] > 0.f) ? 0 : 1;                   // mask pixel outside {gt > 0}
-                    if (want_loss) lsum += (gtv[u] > 0.f) ? (err * err - gtv[u] * gtv[u]) : (err * err);
+                    accv[u][7] += (gtv[u] > 0.f) ? 0.f : 1.f;        // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
+                    if (want_loss) accv[u][6] += (gtv[u] > 0.f) ? (err * err - gtv[u] * gtv[u]) : (err * err);
                     pair_backward(accv[u], A, B, dx, dy, Gv[u], Tb[u], gpix, S, ddelx_dx, ddely_dy);
                 }
             }
         }
     }
 #pragma unroll
-    for (int u = 0; u < N; u++) reduce_store_partial(accv[u], part_out + (size_t)u * NPART, lane);
-    my_lsum += lsum; my_cnt += cnt;
+    for (int u = 0; u < N; u++) reduce_store_partial(accv[u], part_out + (size_t)u * PSTRIDE, lane);
 }
 
 template <int SLOTS>
@@ -226,18 +225,19 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ int s_ngt[MAXV];            // sum_j #{gt > 0}
     __shared__ float s_sgt2[MAXV];         // sum_j sum gt^2
     __shared__ SlotSplats s_sp[SLOTS];
-    __shared__ int s_R[SLOTS], s_nact[SLOTS], s_cnt[SLOTS];
+    __shared__ int s_R[SLOTS], s_nact[SLOTS], s_next;
+    __shared__ float s_jcnt[SLOTS][MAXJ], s_jloss[SLOTS][MAXJ];
     __shared__ float s_lsum[SLOTS][OPT_WARPS];
     __shared__ int s_status;
     extern __shared__ __align__(16) unsigned char dsm[];
-    // dynamic, per slot: partial f32[RCAP*NPART] (24 B/entry) whose storage is first used by the sort's 32-bit words
-    // (dead once the tile lists exist) | list u16 | inv_pos u16 | tile u16 | start u16  => 32 B/entry
+    // dynamic, per slot: partial f32[RCAP*PSTRIDE] (32 B/entry) whose storage is first used by the sort's 32-bit words
+    // (dead once the tile lists exist) | list u16 | inv_pos u16 | tile u16 | start u16  => 40 B/entry
     float* d_part = reinterpret_cast<float*>(dsm);
-    uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)SLOTS * RCAP * NPART);
+    uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)SLOTS * RCAP * PSTRIDE);
     uint16_t* d_inv = d_list + (size_t)SLOTS * RCAP;
     uint16_t* d_tile = d_inv + (size_t)SLOTS * RCAP;
     uint16_t* d_start = d_tile + (size_t)SLOTS * RCAP;
-#define SSB_KEYS32(k) (reinterpret_cast<uint32_t*>(d_part + (size_t)(k) * RCAP * NPART))
+#define SSB_KEYS32(k) (reinterpret_cast<uint32_t*>(d_part + (size_t)(k) * RCAP * PSTRIDE))
 
     // ---------------- load the frame ----------------
     for (int i = tid; i < J * 3; i += OPT_THREADS) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
@@ -301,8 +301,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 #pragma unroll
             for (int k = 0; k < 6; k++) s_cov3d[6 * j + k] = cov[k];
         }
-        if (tid < SLOTS) { s_cnt[tid] = 0; s_slot_view[tid] = (step * acc + tid) % V; }
-        if (tid < SLOTS * OPT_WARPS) (&s_lsum[0][0])[tid] = 0.f;
+        if (tid < SLOTS) s_slot_view[tid] = (step * acc + tid) % V;
+        if (tid == 0) s_next = 0;
         __syncthreads();
         if (tid < SLOTS * J) {
             const int k = tid / J, j = tid % J;
@@ -406,18 +406,19 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         }
         __syncthreads();
 
-        // ============ phase C: tiles.  One warp per active tile, static round-robin ============
+        // ============ phase C: tiles.  One warp per active tile, handed out dynamically (tile lists differ in length);
+        // every result is a per-(tile,Gaussian) record, so the schedule does not influence any sum ============
         {
             int total = 0;
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) total += s_nact[k];
-            float lsum[SLOTS];
-            int lcnt[SLOTS];
-#pragma unroll
-            for (int k = 0; k < SLOTS; k++) { lsum[k] = 0.f; lcnt[k] = 0; }
             const bool want_loss = (step == p.n_steps - 1);
             const float* roi_base = p.roi_data + s_roi_base;
-            for (int item = warp; item < total; item += OPT_WARPS) {
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&s_next, 1);
+                item = __shfl_sync(0xFFFFFFFFu, item, 0);
+                if (item >= total) break;
                 int k = 0, a = item;
 #pragma unroll
                 for (int kk = 0; kk < SLOTS - 1; kk++) { if (k == kk && a >= s_nact[kk]) { a -= s_nact[kk]; k = kk + 1; } }
@@ -430,21 +431,20 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const SlotSplats& sp = s_sp[k];
                 const uint16_t* list = d_list + (size_t)k * RCAP + e0;
                 const float ddelx_dx = s_halfW[v], ddely_dy = s_halfH[v];
-                float my_lsum = 0.f; int my_cnt = 0;
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
-                float* part_out = d_part + ((size_t)k * RCAP + e0) * NPART;
-                if (n == 1) tile_fast<1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
-                else if (n == 2) tile_fast<2>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
-                else if (n == 3) tile_fast<3>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
-                else if (n == 4) tile_fast<4>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane, my_lsum, my_cnt);
+                float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
+                if (n == 1) tile_fast<1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                else if (n == 2) tile_fast<2>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                else if (n == 3) tile_fast<3>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                else if (n == 4) tile_fast<4>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
                 else {
                     // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
                     for (int c0 = 0; c0 < n; c0 += FAST) {
-                        float accv[FAST][NPART];
+                        float accv[FAST][PSTRIDE];
 #pragma unroll
                         for (int u = 0; u < FAST; u++)
 #pragma unroll
-                            for (int q = 0; q < NPART; q++) accv[u][q] = 0.f;
+                            for (int q = 0; q < PSTRIDE; q++) accv[u][q] = 0.f;
                         for (int pass = 0; pass < TILE / 2; pass++) {
                             const int px = lx, py = ly0 + 2 * pass;
                             if (!(px < W && py < H)) continue;          // no warp-collective operation inside the pass loop
@@ -481,53 +481,59 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                 last_g = gpix; last_alpha = alpha;
                                 const int u = e - c0;
                                 if (u >= 0 && u < FAST) {
-                                    if (gt > 0.f) { my_lsum += err * err - gt * gt; } else { my_lsum += err * err; my_cnt++; }
-                                    float w[NPART] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                    float w[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                    w[7] = (gt > 0.f) ? 0.f : 1.f;
+                                    if (want_loss) w[6] = (gt > 0.f) ? (err * err - gt * gt) : (err * err);
                                     pair_backward(w, A, B, dx, dy, G, T, gpix, S, ddelx_dx, ddely_dy);
 #pragma unroll
                                     for (int uu = 0; uu < FAST; uu++)
                                         if (u == uu) {
 #pragma unroll
-                                            for (int q = 0; q < NPART; q++) accv[uu][q] += w[q];
+                                            for (int q = 0; q < PSTRIDE; q++) accv[uu][q] += w[q];
                                         }
                                 }
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < FAST; u++)
-                            if (c0 + u < n) reduce_store_partial(accv[u], part_out + (size_t)(c0 + u) * NPART, lane);   // warp-uniform
+                            if (c0 + u < n) reduce_store_partial(accv[u], part_out + (size_t)(c0 + u) * PSTRIDE, lane);   // warp-uniform
                     }
                 }
-#pragma unroll
-                for (int kk = 0; kk < SLOTS; kk++) if (k == kk) { lsum[kk] += my_lsum; lcnt[kk] += my_cnt; }
-            }
-#pragma unroll
-            for (int k = 0; k < SLOTS; k++) {
-                float a = lsum[k]; int c = lcnt[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xFFFFFFFFu, a, o); c += __shfl_xor_sync(0xFFFFFFFFu, c, o); }
-                if (lane == 0) { s_lsum[k][warp] = a; if (c) atomicAdd(&s_cnt[k], c); }
             }
         }
         __syncthreads();
 
         // ============ phase D: per-Gaussian backward chain + gradient bookkeeping ============
+        // D1: fixed-order (emission order) sum of each Gaussian's per-tile records
+        float s8[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (tid < SLOTS * J) {
+            const int k = tid / J, j = tid % J;
+            const SlotSplats& sp = s_sp[k];
+            if (sp.tiles[j] > 0) {
+                const int o0 = (j == 0) ? 0 : sp.offs[j - 1], o1 = min((int)sp.offs[j], s_R[k]);
+                for (int o = o0; o < o1; o++) {
+                    const float* pp = d_part + ((size_t)k * RCAP + d_inv[(size_t)k * RCAP + o]) * PSTRIDE;
+#pragma unroll
+                    for (int q = 0; q < PSTRIDE; q++) s8[q] += pp[q];
+                }
+            }
+            s_jloss[k][j] = s8[6];
+            s_jcnt[k][j] = s8[7];
+        }
+        __syncthreads();
+        // D2: mask size N of the slot's view, then the chain
         if (tid < SLOTS * J) {
             const int k = tid / J, j = tid % J;
             const int v = (step * acc + k) % V;
             const SlotSplats& sp = s_sp[k];
-            const float invN = 1.0f / (float)(s_ngt[v] + s_cnt[k]);      // mean over the loss mask
+            float extra = 0.f;
+            for (int o = 0; o < J; o++) extra += s_jcnt[k][o];
+            const float invN = 1.0f / ((float)s_ngt[v] + extra);      // mean over the loss mask (N < 2^24: exact)
             float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gop = 0.f;
             if (sp.tiles[j] > 0) {
-                float s6[NPART] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                const int o0 = (j == 0) ? 0 : sp.offs[j - 1], o1 = min((int)sp.offs[j], s_R[k]);
-                for (int o = o0; o < o1; o++) {
-                    const float* pp = d_part + ((size_t)k * RCAP + d_inv[(size_t)k * RCAP + o]) * NPART;
+                float s6[NPART];
 #pragma unroll
-                    for (int q = 0; q < NPART; q++) s6[q] += pp[q];
-                }
-#pragma unroll
-                for (int q = 0; q < NPART; q++) s6[q] *= invN;
+                for (int q = 0; q < NPART; q++) s6[q] = s8[q] * invN;
                 const SplatGrad sg = gaussian_backward(
                     s_xyz[3 * j], s_xyz[3 * j + 1], s_xyz[3 * j + 2], &s_cov3d[6 * j], true,
                     s_act_scale[3 * j], s_act_scale[3 * j + 1], s_act_scale[3 * j + 2], 1.0f,
@@ -583,9 +589,9 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 }
             }
             if (k == SLOTS - 1) {
-                float a = 0.f;
-                for (int w = 0; w < OPT_WARPS; w++) a += s_lsum[k][w];
-                last_loss = (a + s_sgt2[v]) / (float)(s_ngt[v] + s_cnt[k]) + p.cfg.lambda_consistency * cons;
+                float a = 0.f, extra = 0.f;
+                for (int o = 0; o < J; o++) { a += s_jloss[k][o]; extra += s_jcnt[k][o]; }
+                last_loss = (a + s_sgt2[v]) / ((float)s_ngt[v] + extra) + p.cfg.lambda_consistency * cons;
                 if (p.final_loss && step == p.n_steps - 1) p.final_loss[frame] = last_loss;
             }
         }
@@ -621,7 +627,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 }
 
 static size_t opt_dyn_smem(int slots, int rcap) {
-    return (size_t)slots * rcap * (4 * NPART + 2 * 4);
+    return (size_t)slots * rcap * (4 * PSTRIDE + 2 * 4);
 }
 
 }  // namespace ssb
