@@ -62,7 +62,7 @@ typedef struct ssb_cameras {
     const float* projmatrix;     /* [V,16]  full_proj_transform */
     const int*   dims;           /* [V,2] (W,H) per view, or NULL => every view is W0 x H0 */
     const float* tanfov;         /* [V,2] (tanfovx,tanfovy) or NULL => tanfovx0/tanfovy0 */
-    int          W0, H0;
+    int          W0, H0;         /* image size when dims == NULL; otherwise the MAXIMUM over the views (sizes the state) */
     float        tanfovx0, tanfovy0;
     int          antialiasing;   /* 0 in every shipped config */
 } ssb_cameras;

@@ -24,13 +24,13 @@ print(json.dumps({"ms": min(ts), "fps": F / min(ts) * 1e3, "checksum": float(np.
 
 def main():
     from skelsplat_b200 import build
-    variants = [(384, 2), (512, 2), (640, 1), (768, 1), (1024, 1)]
-    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 256), ("panoptic", 1024, 512)]
+    variants = [(1, 1), (2, 1)]      # (SSB_PP_N1, SSB_PP_N2)
+    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512), ("panoptic", 1024, 1024)]
     out = {}
     for thr, cta in variants:
         lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
         if not os.path.exists(lib):
-            build.build(force=True, defines=(f"SSB_OPT_THREADS={thr}", f"SSB_OPT_MIN_CTAS={cta}"), out=lib)
+            build.build(force=True, defines=(f"SSB_PP_N1={thr}", f"SSB_PP_N2={cta}"), out=lib)
     for name, F, rcap in works:
         for thr, cta in variants:
             lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
@@ -44,8 +44,8 @@ def main():
 if __name__ == "__main__":
     if "--build-only" in sys.argv:
         from skelsplat_b200 import build
-        for thr, cta in [(384, 2), (512, 2), (640, 1), (768, 1), (1024, 1)]:
-            build.build(force=True, defines=(f"SSB_OPT_THREADS={thr}", f"SSB_OPT_MIN_CTAS={cta}"),
+        for thr, cta in [(1, 1), (2, 1)]:
+            build.build(force=True, defines=(f"SSB_PP_N1={thr}", f"SSB_PP_N2={cta}"),
                         out=os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so"))
     else:
         main()

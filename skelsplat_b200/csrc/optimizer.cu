@@ -35,6 +35,12 @@ constexpr int OPT_WARPS = OPT_THREADS / 32;
 #ifndef SSB_OPT_MIN_CTAS
 #define SSB_OPT_MIN_CTAS 2
 #endif
+#ifndef SSB_PP_N1           // pixels per lane and trip for tile lists of length 1 / 2 (see tile_fast)
+#define SSB_PP_N1 2
+#endif
+#ifndef SSB_PP_N2
+#define SSB_PP_N2 1
+#endif
 constexpr int MAXJ = 20;
 constexpr int MAXV = 8;
 constexpr int MAX_SLOTS = 4;
@@ -120,12 +126,15 @@ __device__ __forceinline__ void reduce_store_partial(const float (&acc)[PSTRIDE]
 // A tile whose list has exactly N <= FAST Gaussians: everything per-entry lives in registers, loops are fully unrolled.
 // The GT patch addressing is hoisted out of the pass loop: per entry a base offset, a row stride for two rows, and the
 // range of passes whose row falls inside the patch (columns are pass-invariant for a lane).
-template <int N>
+template <int N, int PP>
 __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
                                           const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
                                           int lx, int ly0, int W, int H, float ddelx_dx, float ddely_dy, bool want_loss,
                                           float* __restrict__ part_out, int lane)
 {
+    // PP pixels per lane and loop trip (rows pass and pass + 4 when PP == 2): the two pixels are independent dependency
+    // chains (ILP), share the per-Gaussian shared-memory loads and accumulate into the same per-entry sums.
+    constexpr int NPASS = TILE / 2 / PP;
     int gid[N], goff[N], gw2[N];
     unsigned grange[N];
 #pragma unroll
@@ -148,51 +157,75 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
         for (int q = 0; q < PSTRIDE; q++) accv[u][q] = 0.f;
     if (lx < W) {
-        for (int pass = 0; pass < TILE / 2; pass++) {
-            const int py = ly0 + 2 * pass;
-            if (py >= H) break;
-            const float pxf = (float)lx, pyf = (float)py;
-            // GT values of the listed Gaussians' channels at this pixel: issued first, consumed only in the backward replay,
-            // so the L2 latency hides behind the forward math (a pixel outside a patch reads nothing and gets 0)
-            float gtv[N];
+        const float pxf = (float)lx;
+        for (int pass0 = 0; pass0 < NPASS; pass0++) {
+            if (ly0 + 2 * pass0 >= H) break;
+            // GT values of the listed Gaussians' channels at the lane's pixels: issued first, consumed only in the backward
+            // replay, so the L2 latency hides behind the forward math (a pixel outside a patch reads nothing and gets 0)
+            float gtv[PP][N];
 #pragma unroll
-            for (int u = 0; u < N; u++) {
-                gtv[u] = 0.f;
-                if ((unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8)) gtv[u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
+            for (int q = 0; q < PP; q++) {
+                const int pass = pass0 + q * NPASS;
+#pragma unroll
+                for (int u = 0; u < N; u++) {
+                    gtv[q][u] = 0.f;
+                    if ((unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8)) gtv[q][u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
+                }
             }
-            float al[N], Gv[N], Tb[N];
-            unsigned ok = 0u;
-            float T = 1.0f;
-            bool done = false;
+            float pyf[PP];
+            bool live[PP];
+#pragma unroll
+            for (int q = 0; q < PP; q++) {
+                const int py = ly0 + 2 * (pass0 + q * NPASS);
+                pyf[q] = (float)py;
+                live[q] = py < H;
+            }
+            float al[PP][N], Gv[PP][N], Tb[PP][N], T[PP];
+            unsigned ok = 0u;                                       // bit (q*N + u)
+            bool done[PP];
+#pragma unroll
+            for (int q = 0; q < PP; q++) { T[q] = 1.0f; done[q] = !live[q]; }
             // forward replay (forward.cu:330-386): alpha, G and the transmittance before each accumulated Gaussian
 #pragma unroll
             for (int u = 0; u < N; u++) {
-                al[u] = 0.f; Gv[u] = 0.f; Tb[u] = 0.f;
-                if (!done) {
-                    const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
-                    float dx, dy, G, alpha;
-                    if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf, dx, dy, G, alpha)) {
-                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                        if (test_T < T_EPS) done = true;
-                        else { al[u] = alpha; Gv[u] = G; Tb[u] = T; ok |= 1u << u; T = test_T; }
+                const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
+#pragma unroll
+                for (int q = 0; q < PP; q++) {
+                    al[q][u] = 0.f; Gv[q][u] = 0.f; Tb[q][u] = 0.f;
+                    if (!done[q]) {
+                        float dx, dy, G, alpha;
+                        if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf[q], dx, dy, G, alpha)) {
+                            const float test_T = __fmul_rn(T[q], __fsub_rn(1.0f, alpha));
+                            if (test_T < T_EPS) done[q] = true;
+                            else { al[q][u] = alpha; Gv[q][u] = G; Tb[q][u] = T[q]; ok |= 1u << (q * N + u); T[q] = test_T; }
+                        }
                     }
                 }
             }
             if (ok == 0u) continue;
             // backward replay (backward.cu:536-636) with the one-hot scalar recurrence
-            float S = 0.f, last_alpha = 0.f, last_g = 0.f;
+            float S[PP], last_alpha[PP], last_g[PP];
+#pragma unroll
+            for (int q = 0; q < PP; q++) { S[q] = 0.f; last_alpha[q] = 0.f; last_g[q] = 0.f; }
 #pragma unroll
             for (int u = N - 1; u >= 0; u--) {
-                if ((ok >> u) & 1u) {
+                if (ok & ((1u << u) | (PP == 2 ? (1u << (N + u)) : 0u))) {
                     const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
-                    const float dx = __fsub_rn(A.x, pxf), dy = __fsub_rn(A.y, pyf);
-                    const float err = al[u] * Tb[u] - gtv[u];      // rendered value of channel g minus GT
-                    const float gpix = 2.f * err;                    // unscaled dL/drender (x 1/N later)
-                    S = last_alpha * last_g + (1.f - last_alpha) * S;
-                    last_g = gpix; last_alpha = al[u];
-                    accv[u][7] += (gtv[u] > 0.f) ? 0.f : 1.f;        // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
-                    if (want_loss) accv[u][6] += (gtv[u] > 0.f) ? (err * err - gtv[u] * gtv[u]) : (err * err);
-                    pair_backward(accv[u], A, B, dx, dy, Gv[u], Tb[u], gpix, S, ddelx_dx, ddely_dy);
+                    const float dx = __fsub_rn(A.x, pxf);
+#pragma unroll
+                    for (int q = 0; q < PP; q++) {
+                        if ((ok >> (q * N + u)) & 1u) {
+                            const float dy = __fsub_rn(A.y, pyf[q]);
+                            const float gt = gtv[q][u];
+                            const float err = al[q][u] * Tb[q][u] - gt;   // rendered value of channel g minus GT
+                            const float gpix = 2.f * err;                  // unscaled dL/drender (x 1/N later)
+                            S[q] = last_alpha[q] * last_g[q] + (1.f - last_alpha[q]) * S[q];
+                            last_g[q] = gpix; last_alpha[q] = al[q][u];
+                            accv[u][7] += (gt > 0.f) ? 0.f : 1.f;          // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
+                            if (want_loss) accv[u][6] += (gt > 0.f) ? (err * err - gt * gt) : (err * err);
+                            pair_backward(accv[u], A, B, dx, dy, Gv[q][u], Tb[q][u], gpix, S[q], ddelx_dx, ddely_dy);
+                        }
+                    }
                 }
             }
         }
@@ -201,10 +234,12 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
     for (int u = 0; u < N; u++) reduce_store_partial(accv[u], part_out + (size_t)u * PSTRIDE, lane);
 }
 
-template <int SLOTS>
-__global__ void __launch_bounds__(OPT_THREADS, SSB_OPT_MIN_CTAS)
+// NT threads per CTA: 512 with two CTAs per SM, or 1024 with one when the binning state (r_capacity) is too large for two.
+template <int SLOTS, int NT>
+__global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : SSB_OPT_MIN_CTAS))
 optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ StepTable tab)
 {
+    constexpr int NW = NT / 32;
     const int J = p.cfg.J, V = p.cfg.V, RCAP = p.cfg.r_capacity;
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,7 +262,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ SlotSplats s_sp[SLOTS];
     __shared__ int s_R[SLOTS], s_nact[SLOTS], s_next;
     __shared__ float s_jcnt[SLOTS][MAXJ], s_jloss[SLOTS][MAXJ];
-    __shared__ float s_lsum[SLOTS][OPT_WARPS];
+    __shared__ float s_lsum[SLOTS][NW];
     __shared__ int s_status;
     extern __shared__ __align__(16) unsigned char dsm[];
     // dynamic, per slot: partial f32[RCAP*PSTRIDE] (32 B/entry) whose storage is first used by the sort's 32-bit words
@@ -240,12 +275,12 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 #define SSB_KEYS32(k) (reinterpret_cast<uint32_t*>(d_part + (size_t)(k) * RCAP * PSTRIDE))
 
     // ---------------- load the frame ----------------
-    for (int i = tid; i < J * 3; i += OPT_THREADS) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
-    for (int i = tid; i < J * 4; i += OPT_THREADS) s_rot[i] = p.rotation_raw[(size_t)frame * J * 4 + i];
-    for (int i = tid; i < J; i += OPT_THREADS) s_opa[i] = p.opacity_raw[(size_t)frame * J + i];
-    for (int i = tid; i < J * 11; i += OPT_THREADS) { s_m[i] = 0.f; s_v[i] = 0.f; s_grad[i] = 0.f; }
-    for (int i = tid; i < MAXV * MAXJ * 3; i += OPT_THREADS) (&s_accg[0][0])[i] = 0.f;
-    for (int i = tid; i < V * 16; i += OPT_THREADS) { s_view[i / 16][i % 16] = p.cams.viewmatrix[i]; s_proj[i / 16][i % 16] = p.cams.projmatrix[i]; }
+    for (int i = tid; i < J * 3; i += NT) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
+    for (int i = tid; i < J * 4; i += NT) s_rot[i] = p.rotation_raw[(size_t)frame * J * 4 + i];
+    for (int i = tid; i < J; i += NT) s_opa[i] = p.opacity_raw[(size_t)frame * J + i];
+    for (int i = tid; i < J * 11; i += NT) { s_m[i] = 0.f; s_v[i] = 0.f; s_grad[i] = 0.f; }
+    for (int i = tid; i < MAXV * MAXJ * 3; i += NT) (&s_accg[0][0])[i] = 0.f;
+    for (int i = tid; i < V * 16; i += NT) { s_view[i / 16][i % 16] = p.cams.viewmatrix[i]; s_proj[i / 16][i % 16] = p.cams.projmatrix[i]; }
     if (tid < V) {
         const int W = p.cams.dims ? p.cams.dims[2 * tid] : p.cams.W0, H = p.cams.dims ? p.cams.dims[2 * tid + 1] : p.cams.H0;
         const float tfx = p.cams.tanfov ? p.cams.tanfov[2 * tid] : p.cams.tanfovx0, tfy = p.cams.tanfov ? p.cams.tanfov[2 * tid + 1] : p.cams.tanfovy0;
@@ -255,7 +290,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         s_fx[tid] = __fdiv_rn((float)W, __fmul_rn(2.0f, tfx));
         s_ngt[tid] = 0; s_sgt2[tid] = 0.f;
     }
-    for (int i = tid; i < V * J; i += OPT_THREADS) {
+    for (int i = tid; i < V * J; i += NT) {
         const int v = i / J, j = i % J;
         const size_t o = ((size_t)frame * V + v) * J + j;
         s_roi[v][j] = make_int4(p.roi_rect[4 * o], p.roi_rect[4 * o + 1], p.roi_rect[4 * o + 2], p.roi_rect[4 * o + 3]);
@@ -270,13 +305,13 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         for (int j = 0; j < J; j++) {
             const int n = s_roi[v][j].z * s_roi[v][j].w;
             const float* d = p.roi_data + s_roi_base + s_roi_rel[v][j];
-            for (int i = tid; i < n; i += OPT_THREADS) { const float g = __ldg(d + i); if (g > 0.f) { cnt++; sq = fmaf(g, g, sq); } }
+            for (int i = tid; i < n; i += NT) { const float g = __ldg(d + i); if (g > 0.f) { cnt++; sq = fmaf(g, g, sq); } }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); }
         if (lane == 0) { s_lsum[0][warp] = sq; atomicAdd(&s_ngt[v], cnt); }
         __syncthreads();
-        if (tid == 0) { float a = 0.f; for (int w = 0; w < OPT_WARPS; w++) a += s_lsum[0][w]; s_sgt2[v] = a; }
+        if (tid == 0) { float a = 0.f; for (int w = 0; w < NW; w++) a += s_lsum[0][w]; s_sgt2[v] = a; }
         __syncthreads();
     }
 
@@ -336,7 +371,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         }
         // 32-bit sort words: tile (17 bits) | depth rank of the Gaussian (5) | emission index (10).  (tile, rank) is unique per
         // entry, so sorting the words reproduces the reference's stable (tile | depth bits) order; the emission index rides along.
-        for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) SSB_KEYS32(i >> lgsort)[i & (nsort - 1)] = 0xFFFFFFFFu;
+        for (int i = tid; i < SLOTS * nsort; i += NT) SSB_KEYS32(i >> lgsort)[i & (nsort - 1)] = 0xFFFFFFFFu;
         if (tid < SLOTS * J) {      // depth rank: position of (depth bits, id) among the slot's Gaussians
             const int k = tid / J, j = tid % J;
             SlotSplats& sp = s_sp[k];
@@ -366,7 +401,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         // bitonic sort of all slots at once (independent sub-arrays of length nsort)
         for (int kk = 2; kk <= nsort; kk <<= 1) {
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                for (int i = tid; i < SLOTS * (nsort >> 1); i += OPT_THREADS) {
+                for (int i = tid; i < SLOTS * (nsort >> 1); i += NT) {
                     // i enumerates the compare-exchange pairs: insert a 0 bit at position log2(jj)
                     const int k = i >> (lgsort - 1), q = i & ((nsort >> 1) - 1);
                     const int e = ((q & ~(jj - 1)) << 1) | (q & (jj - 1));
@@ -377,7 +412,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 __syncthreads();
             }
         }
-        for (int i = tid; i < SLOTS * nsort; i += OPT_THREADS) {
+        for (int i = tid; i < SLOTS * nsort; i += NT) {
             const int k = i >> lgsort, e = i & (nsort - 1);
             if (e < s_R[k]) {
                 const uint32_t key = SSB_KEYS32(k)[e];
@@ -433,10 +468,10 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const float ddelx_dx = s_halfW[v], ddely_dy = s_halfH[v];
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
-                if (n == 1) tile_fast<1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
-                else if (n == 2) tile_fast<2>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
-                else if (n == 3) tile_fast<3>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
-                else if (n == 4) tile_fast<4>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                if (n == 1) tile_fast<1, SSB_PP_N1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                else if (n == 2) tile_fast<2, SSB_PP_N2>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                else if (n == 3) tile_fast<3, 1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+                else if (n == 4) tile_fast<4, 1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
                 else {
                     // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
                     for (int c0 = 0; c0 < n; c0 += FAST) {
@@ -619,9 +654,9 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     }
 
     // ---------------- write back ----------------
-    for (int i = tid; i < J * 3; i += OPT_THREADS) { p.xyz[(size_t)frame * J * 3 + i] = s_xyz[i]; p.scaling_raw[(size_t)frame * J * 3 + i] = s_scal[i]; }
-    for (int i = tid; i < J * 4; i += OPT_THREADS) p.rotation_raw[(size_t)frame * J * 4 + i] = s_rot[i];
-    for (int i = tid; i < J; i += OPT_THREADS) p.opacity_raw[(size_t)frame * J + i] = s_opa[i];
+    for (int i = tid; i < J * 3; i += NT) { p.xyz[(size_t)frame * J * 3 + i] = s_xyz[i]; p.scaling_raw[(size_t)frame * J * 3 + i] = s_scal[i]; }
+    for (int i = tid; i < J * 4; i += NT) p.rotation_raw[(size_t)frame * J * 4 + i] = s_rot[i];
+    for (int i = tid; i < J; i += NT) p.opacity_raw[(size_t)frame * J + i] = s_opa[i];
     if (tid == 0 && p.status) p.status[frame] = s_status;
     (void)last_loss;
 }
@@ -678,11 +713,19 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
     cudaStream_t stream = (cudaStream_t)stream_;
     const int slots = cfg->accumulation_steps;
     const size_t smem = opt_dyn_smem(slots, cfg->r_capacity);
+    // two 512-thread CTAs per SM when their shared memory fits (227 KB/SM), else one 1024-thread CTA: 32 warps/SM either way
+    const bool big = (2 * (smem + 17 * 1024) > 227 * 1024);
 #define SSB_LAUNCH_OPT(S)                                                                                         \
     {                                                                                                             \
-        if (cudaFuncSetAttribute(optimize_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-            return ssb_set_cuda_error(cudaGetLastError());                                                        \
-        optimize_kernel<S><<<n_frames, OPT_THREADS, smem, stream>>>(p, tab);                                      \
+        if (big) {                                                                                                \
+            if (cudaFuncSetAttribute(optimize_kernel<S, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+                return ssb_set_cuda_error(cudaGetLastError());                                                    \
+            optimize_kernel<S, 1024><<<n_frames, 1024, smem, stream>>>(p, tab);                                   \
+        } else {                                                                                                  \
+            if (cudaFuncSetAttribute(optimize_kernel<S, OPT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+                return ssb_set_cuda_error(cudaGetLastError());                                                    \
+            optimize_kernel<S, OPT_THREADS><<<n_frames, OPT_THREADS, smem, stream>>>(p, tab);                     \
+        }                                                                                                         \
     }
     switch (slots) {
         case 1: SSB_LAUNCH_OPT(1) break;

@@ -612,9 +612,9 @@ static int next_pow2(int x) { int n = 1; while (n < x) n <<= 1; return n; }
         default: return SSB_ERR_UNSUPPORTED;                        \
     }
 
-static void max_dims(const ssb_cameras* cams, const int* dims_host, int& Wmax, int& Hmax) {
+// W0 x H0 is the largest view of the rig (per-view sizes, if any, live in cams->dims on the device): it sizes the state.
+static void max_dims(const ssb_cameras* cams, int& Wmax, int& Hmax) {
     Wmax = cams->W0; Hmax = cams->H0;
-    (void)dims_host;
 }
 
 }  // namespace ssb
@@ -656,7 +656,7 @@ int ssb_rasterize_forward(int n_frames, const ssb_gaussians* g, const ssb_camera
     const int B = n_frames * cams->n_views;
     if (B == 0) return SSB_OK;
     int Wmax, Hmax;
-    max_dims(cams, nullptr, Wmax, Hmax);
+    max_dims(cams, Wmax, Hmax);
     const StateLayout L = state_layout(g->P, Wmax, Hmax, rcap);
     const int n2 = next_pow2(rcap);
     const size_t smem = (size_t)n2 * 12 + (size_t)(g->P > 0 ? g->P : 1) * 4 + 16;
@@ -692,7 +692,7 @@ int ssb_rasterize_backward(int n_frames, const ssb_gaussians* g, const ssb_camer
     const int B = n_frames * cams->n_views;
     if (B == 0 || g->P == 0) return SSB_OK;
     int Wmax, Hmax;
-    max_dims(cams, nullptr, Wmax, Hmax);
+    max_dims(cams, Wmax, Hmax);
     const StateLayout L = state_layout(g->P, Wmax, Hmax, rcap);
     const size_t stride = ssb_backward_scratch_bytes(g->C, rcap) / sizeof(float);
     // CTAs per view looping over that view's active tiles: enough to fill 148 SMs at small B

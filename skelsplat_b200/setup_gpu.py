@@ -55,11 +55,12 @@ def generate_heatmap_rois_gpu(cfg: SceneConfig, vm, pm, dims, tanfov, Wmax, Hmax
 def pack_sequence_gpu(cfg: SceneConfig, cams, poses_2d, poses_init=None, device="cuda") -> PackedSequence:
     """detections [F,V,J,2] (+ optional initial poses) -> PackedSequence, entirely on the GPU.
     Without ``poses_init`` the initial guess is the DLT triangulation of the detections (BASELINE config 1)."""
-    poses_2d = np.asarray(poses_2d)
-    F = poses_2d.shape[0]
-    d2 = torch.as_tensor(poses_2d).to(device)
+    d2 = (poses_2d if torch.is_tensor(poses_2d) else torch.as_tensor(np.asarray(poses_2d))).to(device)
+    F = d2.shape[0]
     if poses_init is None:
         init = triangulate_dlt([c.P3x4() for c in cams], d2, device).to(torch.float32)
+    elif torch.is_tensor(poses_init):
+        init = poses_init.to(device=device, dtype=torch.float32)
     else:
         init = torch.as_tensor(np.asarray(poses_init, np.float32)).to(device)
     _, scal, rot, opa = initial_raw_state(cfg, np.zeros((F, cfg.n_joints, 3), np.float32))

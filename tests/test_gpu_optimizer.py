@@ -151,3 +151,17 @@ def test_streaming_pipeline_equals_resident_run():
     for a, b in zip(outs, refs):
         assert np.array_equal(a, b)
     assert so.launches == 3
+
+
+def test_capacity_retry_is_transparent_and_exact():
+    """Frames whose (Gaussian,tile) lists outgrow the default capacity are re-run from their initial state with a doubled
+    capacity; the result equals a run that had the larger capacity from the start."""
+    from dataclasses import replace
+    cfg = replace(configs.H36M, scaling=3.6)                       # larger splats: ~340 pairs per view > default 256
+    seq = synthetic.make_sequence(cfg, 3, seed=17)
+    assert trainer.default_r_capacity(cfg) == 256
+    with pytest.raises(Exception, match="r_capacity"):
+        trainer.optimize_sequence(seq, DEV, iterations=40, r_capacity=256)
+    auto = trainer.optimize_sequence(seq, DEV, iterations=40)       # default capacity + automatic retry
+    big = trainer.optimize_sequence(seq, DEV, iterations=40, r_capacity=512)
+    assert np.array_equal(auto, big)
