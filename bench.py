@@ -235,6 +235,7 @@ def run_ours(args):
         m2["roofline"]["algorithmic_bytes_per_launch"] = m2["roofline"]["algorithmic_bytes_per_view"] * m2["views_per_launch"]
     cpu = guarded(cpu_baseline, cfg, seq) if world == 1 else None
     setup = guarded(bench_setup, torch, cfg, seq, dev) if world == 1 else None
+    dense_ctx = guarded(bench_dropin_and_losses, torch, cfg, seq, dev, hbm_peak) if world == 1 else None
     from skelsplat_b200.trainer import mpjpe
     line = {
         "metric": "optimised_frames_per_sec", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -245,7 +246,7 @@ def run_ours(args):
                    "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3), "includes": "trainer.StreamingOptimizer: per step pinned-host -> device copy of initial poses/params + GT heatmap ROIs, fused optimiser, device -> host copy of final poses + status; copies of step i+1 overlap the kernel of step i"},
-        "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "setup_gpu": setup, "cpu_baseline": cpu,
+        "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "setup_gpu": setup, "dense_surface": dense_ctx, "cpu_baseline": cpu,
         "accuracy": {"mpjpe_init_mm": round(mpjpe(host["xyz"], gt), 3), "mpjpe_final_mm": round(mpjpe(final, gt), 3)},
     }
     print(json.dumps(line), flush=True)
@@ -324,6 +325,49 @@ def bench_setup(torch, cfg, seq, dev, F=2048):
     return {"frames": F, "gpu_dlt_frames_per_s": round(F / t_dlt, 1), "gpu_heatmap_roi_frames_per_s": round(F / t_roi, 1),
             "host_numpy_dlt_frames_per_s": round(cpu_dlt, 1), "host_numpy_heatmap_roi_frames_per_s": round(cpu_roi, 2),
             "note": "per-frame setup (SURVEY 8 rows f-3, f-1); heatmap figure includes buffer allocation and its one host sync"}
+
+
+def bench_dropin_and_losses(torch, cfg, seq, dev, hbm_peak):
+    """Context numbers for the dense drop-in surface: (1) train.py's per-iteration loop on the drop-in packages (dense images,
+    torch Adam) -- what swapping the packages alone buys; (2) fused l2_gaussian fwd+bwd and (3) fused SSIM against their HBM
+    streams.  fused-ssim's README plots (RTX 3080 Ti): ~3.0 ms / training iteration and ~1.3 ms inference at B=5, CH=1, 1500x1500."""
+    from skelsplat_b200.training import optimise_frame_dropin
+    from skelsplat_b200 import loss_utils as LU
+    from fused_ssim import fused_ssim
+    out = {}
+    optimise_frame_dropin(seq.frames[0], seq.cameras, cfg, device=dev, iterations=8)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    optimise_frame_dropin(seq.frames[1], seq.cameras, cfg, device=dev, iterations=100)
+    torch.cuda.synchronize()
+    out["dropin_loop_frames_per_s"] = round(1.0 / ((time.perf_counter() - t0) * cfg.iterations / 100), 3)
+
+    def ev(fn, reps=10):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+    n = 8 * 17 * 1000 * 1000                      # 8 views' worth: 544 MB per tensor > L2
+    r = torch.rand(n, device=dev).requires_grad_(True); g = torch.rand(n, device=dev)
+
+    def loss_step():
+        r.grad = None
+        l, _ = LU.l2_loss_gaussian(r, g, None, want_error=False)
+        l.backward()
+    ms = ev(loss_step)
+    out["l2_gaussian_fwd_bwd"] = {"elements": n, "ms": round(ms, 3), "algorithmic_bytes": 20 * n,
+                                  "achieved_gbs": round(20 * n / ms / 1e6, 1), "frac_of_hbm_peak": round(20 * n / ms / 1e6 / hbm_peak, 3),
+                                  "note": "fwd 2 loads, bwd 2 loads + 1 store per element; includes torch autograd glue"}
+    a = torch.rand(5, 1, 1500, 1500, device=dev).requires_grad_(True); b = torch.rand(5, 1, 1500, 1500, device=dev)
+
+    def ssim_train():
+        a.grad = None
+        fused_ssim(a, b).backward()
+    out["fused_ssim_5x1x1500x1500"] = {"train_iter_ms": round(ev(ssim_train), 3),
+                                       "inference_ms": round(ev(lambda: fused_ssim(a.detach(), b, train=False)), 3),
+                                       "published_rtx3080ti_ms": {"train_iter": 3.0, "inference": 1.3}}
+    return out
 
 
 # ----------------------------------------------------------------------------------------- CPU baseline
