@@ -24,13 +24,13 @@ print(json.dumps({"ms": min(ts), "fps": F / min(ts) * 1e3, "checksum": float(np.
 
 def main():
     from skelsplat_b200 import build
-    variants = [(1, 1), (2, 1)]      # (SSB_PP_N1, SSB_PP_N2)
-    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512), ("panoptic", 1024, 1024)]
+    variants = [(0, 0), (1, 0), (0, 1), (1, 1)]      # (SSB_VCULL, repeat)
+    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512)]
     out = {}
     for thr, cta in variants:
         lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
         if not os.path.exists(lib):
-            build.build(force=True, defines=(f"SSB_PP_N1={thr}", f"SSB_PP_N2={cta}"), out=lib)
+            build.build(force=True, defines=(f"SSB_VCULL={thr}",), out=lib)
     for name, F, rcap in works:
         for thr, cta in variants:
             lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
@@ -44,8 +44,8 @@ def main():
 if __name__ == "__main__":
     if "--build-only" in sys.argv:
         from skelsplat_b200 import build
-        for thr, cta in [(1, 1), (2, 1)]:
-            build.build(force=True, defines=(f"SSB_PP_N1={thr}", f"SSB_PP_N2={cta}"),
+        for thr, cta in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+            build.build(force=True, defines=(f"SSB_VCULL={thr}",),
                         out=os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so"))
     else:
         main()

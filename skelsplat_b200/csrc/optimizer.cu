@@ -41,6 +41,10 @@ constexpr int OPT_WARPS = OPT_THREADS / 32;
 #ifndef SSB_PP_N2
 #define SSB_PP_N2 1
 #endif
+#ifndef SSB_VCULL            // exact vertical-band culling of (pass, entry) work in tile_fast: bitwise-identical results,
+                             // but measured 8 % SLOWER on B200 (range tests + register pressure > skipped work): off
+#define SSB_VCULL 0
+#endif
 constexpr int MAXJ = 20;
 constexpr int MAXV = 8;
 constexpr int MAX_SLOTS = 4;
@@ -126,21 +130,29 @@ __device__ __forceinline__ void reduce_store_partial(const float (&acc)[PSTRIDE]
 // A tile whose list has exactly N <= FAST Gaussians: everything per-entry lives in registers, loops are fully unrolled.
 // The GT patch addressing is hoisted out of the pass loop: per entry a base offset, a row stride for two rows, and the
 // range of passes whose row falls inside the patch (columns are pass-invariant for a lane).
-template <int N, int PP>
+template <int N, int PP, bool WANT_LOSS>
 __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
                                           const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
-                                          int lx, int ly0, int W, int H, float ddelx_dx, float ddely_dy, bool want_loss,
+                                          int lx, int ly0, int W, int H, float ddelx_dx, float ddely_dy,
                                           float* __restrict__ part_out, int lane)
 {
+    // WANT_LOSS: only the last optimiser step reports a loss; elsewhere its accumulator folds away (one register per entry).
     // PP pixels per lane and loop trip (rows pass and pass + 4 when PP == 2): the two pixels are independent dependency
     // chains (ILP), share the per-Gaussian shared-memory loads and accumulate into the same per-entry sums.
     constexpr int NPASS = TILE / 2 / PP;
     int gid[N], goff[N], gw2[N];
-    unsigned grange[N];
+    unsigned grange[N], vrange[N];
+    const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
 #pragma unroll
     for (int u = 0; u < N; u++) {
         const int g = list[u];
         gid[u] = g;
+        {   // passes whose two rows can intersect the Gaussian's alpha >= 1/255 band (warp-uniform, conservative)
+            const float gy = sp.geoA[g].y, ey = sp.geoB[g].w;
+            const float flo = ceilf((gy - ey - (float)ty0 - 1.0f) * 0.5f), fhi = floorf((gy + ey - (float)ty0) * 0.5f);
+            const int vlo = (int)fmaxf(flo, 0.0f), vhi = (int)fminf(fhi, (float)(TILE / 2 - 1));
+            vrange[u] = SSB_VCULL ? ((vhi >= vlo) ? ((unsigned)vlo | ((unsigned)(vhi - vlo + 1) << 8)) : 0u) : (unsigned)((TILE / 2) << 8);
+        }
         const int4 roi = roi_v[g];
         const int rx = lx - roi.x, ry0 = ly0 - roi.y;
         int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                 // first pass with ry0 + 2*pass >= 0
@@ -169,7 +181,8 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if ((unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8)) gtv[q][u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
+                    if ((unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8) && (unsigned)(pass - (int)(vrange[u] & 255u)) < (vrange[u] >> 8))
+                        gtv[q][u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
                 }
             }
             float pyf[PP];
@@ -192,7 +205,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int q = 0; q < PP; q++) {
                     al[q][u] = 0.f; Gv[q][u] = 0.f; Tb[q][u] = 0.f;
-                    if (!done[q]) {
+                    if (!done[q] && (unsigned)(pass0 + q * NPASS - (int)(vrange[u] & 255u)) < (vrange[u] >> 8)) {
                         float dx, dy, G, alpha;
                         if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf[q], dx, dy, G, alpha)) {
                             const float test_T = __fmul_rn(T[q], __fsub_rn(1.0f, alpha));
@@ -222,7 +235,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
                             S[q] = last_alpha[q] * last_g[q] + (1.f - last_alpha[q]) * S[q];
                             last_g[q] = gpix; last_alpha[q] = al[q][u];
                             accv[u][7] += (gt > 0.f) ? 0.f : 1.f;          // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
-                            if (want_loss) accv[u][6] += (gt > 0.f) ? (err * err - gt * gt) : (err * err);
+                            if (WANT_LOSS) accv[u][6] += (gt > 0.f) ? (err * err - gt * gt) : (err * err);
                             pair_backward(accv[u], A, B, dx, dy, Gv[q][u], Tb[q][u], gpix, S[q], ddelx_dx, ddely_dy);
                         }
                     }
@@ -347,7 +360,11 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                              p.cfg.antialiasing != 0);
             SlotSplats& sp = s_sp[k];
             sp.geoA[j] = make_float4(s.px, s.py, s.opac, 0.f);
-            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, 0.f);
+            // rows farther than ey from the centre cannot reach alpha >= 1/255: max_dx power = -0.5 dy^2 det/conx >= -5.55
+            // (same bound as pair_alpha's early-out; opacity <= 1 here) -- +1 px of slack for rounding
+            const float cdet = s.conx * s.conz - s.cony * s.cony;
+            const float ey = (cdet > 0.f && s.conx > 0.f) ? sqrtf(11.1f * s.conx / cdet) + 1.0f : 1e9f;
+            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, ey);
             sp.depth_bits[j] = __float_as_uint(s.depth);
             sp.rx0[j] = (uint16_t)s.rect.x0; sp.ry0[j] = (uint16_t)s.rect.y0; sp.rx1[j] = (uint16_t)s.rect.x1; sp.ry1[j] = (uint16_t)s.rect.y1;
             sp.tiles[j] = (uint16_t)min(s.tiles, 65535u);
@@ -468,10 +485,16 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const float ddelx_dx = s_halfW[v], ddely_dy = s_halfH[v];
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
-                if (n == 1) tile_fast<1, SSB_PP_N1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
-                else if (n == 2) tile_fast<2, SSB_PP_N2>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
-                else if (n == 3) tile_fast<3, 1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
-                else if (n == 4) tile_fast<4, 1>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, want_loss, part_out, lane);
+#define SSB_TILE_FAST(NN, PPP)                                                                                                   \
+                {                                                                                                                \
+                    if (want_loss) tile_fast<NN, PPP, true>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, part_out, lane);   \
+                    else tile_fast<NN, PPP, false>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, part_out, lane);          \
+                }
+                if (n == 1) SSB_TILE_FAST(1, SSB_PP_N1)
+                else if (n == 2) SSB_TILE_FAST(2, SSB_PP_N2)
+                else if (n == 3) SSB_TILE_FAST(3, 1)
+                else if (n == 4) SSB_TILE_FAST(4, 1)
+#undef SSB_TILE_FAST
                 else {
                     // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
                     for (int c0 = 0; c0 < n; c0 += FAST) {

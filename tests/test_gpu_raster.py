@@ -229,7 +229,7 @@ def test_many_gaussians_and_large_lists_bit_exact():
     case["features"] = rng.uniform(size=(P, C)).astype(np.float32)
     (color, radii, invd, st), W, H = mine_forward(case, 0, r_capacity=16384)
     of = oracle_forward(case, 0)
-    assert of["R"] > 3000 and st.header()[2] == 0
+    assert of["R"] > 2000 and st.header()[2] == 0
     assert_stages_equal(st.parse(0), of, radii[0].cpu().numpy(), of["radii"])
     assert relerr(color[0].cpu().numpy(), of["color"]) < TOL
     dL = synthetic_dL(of["color"].shape, 3)
