@@ -221,27 +221,33 @@ bin_kernel(ssb_gaussians g, ssb_cameras cams, int rcap, int n2, StateLayout L, i
 
 // ------------------------------------------------------------------------------------------ render fwd
 // The dense contract says "a freshly written [C,H,W] image", and >97 % of it is zeros.  Two kernels:
-//   fill_zero_kernel      pure streaming 128-bit stores over each view's image + inverse depth (HBM-write bound);
+//   fill_zero_kernel      pure streaming 256-bit stores over each view's image + inverse depth (HBM-write bound);
 //   render_active_kernel  CTAs loop over the view's ACTIVE tiles only (compact list from bin_kernel) and overwrite
 //                         them with the composited values (~3 % of the bytes are written twice).
 // The reference writes every element twice (torch::full, then renderCUDA on all tiles) plus 12 B/pixel of side
 // buffers (final_T, n_contrib, ranges sized W*H); here backward recomputes those on the active tiles instead.
-constexpr int FILL_THREADS = 256;
+constexpr int FILL_THREADS = 512;
+
+// 256-bit global store (STG.E.256, new on sm_100): measured 7.23 TB/s for a pure fill at 148x64 CTAs x 512 threads
+// vs 5.99 TB/s for the 128-bit version at 148x8 x 256 (scripts/fillbench.cu; cudaMemsetAsync reaches 7.18 TB/s).
+__device__ __forceinline__ void store_zero_256(float* q) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "l"(q), "f"(0.0f) : "memory");
+}
 
 __device__ __forceinline__ void fill_zero(float* __restrict__ p, size_t n, size_t g, size_t stride) {
-    size_t head = ((16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15) >> 2;
+    size_t head = ((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2;      // floats before 32-B alignment
     if (head > n) head = n;
     if (g < head) p[g] = 0.f;
-    float4* p4 = reinterpret_cast<float4*>(p + head);
-    const size_t n4 = (n - head) >> 2;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* p8 = p + head;
+    const size_t n8 = (n - head) >> 3;
     size_t i = g;
-    for (; i + 3 * stride < n4; i += 4 * stride) {      // 4 independent 16-B stores in flight per thread
-        p4[i] = z; p4[i + stride] = z; p4[i + 2 * stride] = z; p4[i + 3 * stride] = z;
+    for (; i + stride < n8; i += 2 * stride) {      // 2 independent 32-B stores in flight per thread
+        store_zero_256(p8 + 8 * i);
+        store_zero_256(p8 + 8 * (i + stride));
     }
-    for (; i < n4; i += stride) p4[i] = z;
-    const size_t tail = head + (n4 << 2) + g;
-    if (tail < n) p[tail] = 0.f;
+    for (; i < n8; i += stride) store_zero_256(p8 + 8 * i);
+    const size_t tail = head + (n8 << 3) + g;       // < 8 floats left
+    if (g < 8 && tail < n) p[tail] = 0.f;
 }
 
 __global__ void __launch_bounds__(FILL_THREADS)
@@ -665,9 +671,11 @@ int ssb_rasterize_forward(int n_frames, const ssb_gaussians* g, const ssb_camera
             return ssb_set_cuda_error(cudaGetLastError());
     }
     bin_kernel<<<B, BIN_THREADS, smem, stream>>>(*g, *cams, rcap, n2, L, Wmax, Hmax, (char*)state, radii);
-    // zero fill: enough CTAs to saturate HBM writes at any batch size (148 SMs x 8), at most one 16-B store set per thread
-    int fx = (148 * 8 + B - 1) / B;
-    fx = fx < 8 ? 8 : fx;
+    // zero fill: ~148x64 CTAs in total (the fill microbench keeps gaining up to there), but at least 2 stores per thread
+    int fx = (148 * 64 + B - 1) / B;
+    const long long work = ((long long)g->C * Wmax * Hmax / 8 + 2 * FILL_THREADS - 1) / (2 * FILL_THREADS);
+    if (fx > work) fx = (int)work;
+    fx = fx < 1 ? 1 : fx;
     fill_zero_kernel<<<dim3(fx, B), FILL_THREADS, 0, stream>>>(*cams, g->C, out_color, color_offsets, out_invdepth, invdepth_offsets);
     if (g->P > 0) {
         int G = (148 * 8 + B - 1) / B;
