@@ -41,10 +41,8 @@ constexpr int OPT_WARPS = OPT_THREADS / 32;
 #ifndef SSB_PP_N2
 #define SSB_PP_N2 1
 #endif
-#ifndef SSB_VCULL            // exact vertical-band culling of (pass, entry) work in tile_fast: bitwise-identical results,
-                             // but measured 8 % SLOWER on B200 (range tests + register pressure > skipped work): off
-#define SSB_VCULL 0
-#endif
+// (Tried and removed: exact vertical-band culling of (pass, entry) work -- bitwise-identical results but 8 % slower, the
+//  range tests and their registers cost more than the skipped rows save)
 constexpr int MAXJ = 20;
 constexpr int MAXV = 8;
 constexpr int MAX_SLOTS = 4;
@@ -102,21 +100,33 @@ struct SlotSplats {
     uint8_t rank[MAXJ], of_rank[MAXJ];     // depth rank of each Gaussian ((depth bits, id) order) and its inverse
 };
 
-// Per (pixel, Gaussian) backward terms (backward.cu:600-636) given alpha, G, T before the Gaussian, the pixel deltas,
-// the unscaled dL/drender of the Gaussian's own channel (gpix) and the recurrence value S.
-__device__ __forceinline__ void pair_backward(float (&acc)[PSTRIDE], const float4 A, const float4 B, float dx, float dy, float G,
-                                              float Tb, float gpix, float S, float ddelx_dx, float ddely_dy) {
-    const float dL_dalpha = (gpix - S) * Tb;
-    const float dL_dG = A.z * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * B.x - gdy * B.y;
-    const float dG_ddely = -gdy * B.z - gdx * B.y;
-    acc[0] += dL_dG * dG_ddelx * ddelx_dx;
-    acc[1] += dL_dG * dG_ddely * ddely_dy;
-    acc[2] += -0.5f * gdx * dx * dL_dG;
-    acc[3] += -0.5f * gdx * dy * dL_dG;
-    acc[4] += -0.5f * gdy * dy * dL_dG;
-    acc[5] += G * dL_dalpha;
+// Per (pixel, Gaussian) backward terms (backward.cu:600-636), accumulated as RAW moment sums: with
+//   w = G * dL/dalpha / 2 = G * (err - S) * T      (err = rendered - gt of the Gaussian's own channel, S the recurrence of
+//                                                    DESIGN.md 4.1 run on err instead of 2 err)
+// a record holds  sum w dx, sum w dy, sum w dx^2, sum w dx dy, sum w dy^2, sum w.  Everything that is constant per Gaussian
+// (opacity, conic, the 2 of the MSE derivative, -1/2, the NDC scale, 1/N) is applied ONCE after the per-tile records are
+// summed (records_to_grads) instead of once per pixel: 11 instead of ~25 instructions per (pixel, Gaussian).
+__device__ __forceinline__ void pair_backward(float (&acc)[PSTRIDE], float dx, float dy, float G, float Tb, float err, float S) {
+    const float w = G * ((err - S) * Tb);
+    const float wx = w * dx, wy = w * dy;
+    acc[0] += wx;
+    acc[1] += wy;
+    acc[2] = fmaf(wx, dx, acc[2]);
+    acc[3] = fmaf(wx, dy, acc[3]);
+    acc[4] = fmaf(wy, dy, acc[4]);
+    acc[5] += w;
+}
+
+// Raw moment sums of one Gaussian -> dL/dmean2D (x, y), dL/dconic (xx, xy, yy), dL/dopacity  (all still to be scaled by 1/N).
+__device__ __forceinline__ void records_to_grads(const float (&r)[PSTRIDE], float opac, float conx, float cony, float conz,
+                                                 float ddelx_dx, float ddely_dy, float (&out)[NPART]) {
+    const float t = 2.f * opac * r[0], u = 2.f * opac * r[1];       // sum dL/dG G dx, sum dL/dG G dy
+    out[0] = -(conx * t + cony * u) * ddelx_dx;
+    out[1] = -(conz * u + cony * t) * ddely_dy;
+    out[2] = -opac * r[2];
+    out[3] = -opac * r[3];
+    out[4] = -opac * r[4];
+    out[5] = 2.f * r[5];
 }
 
 // One reduction per (tile, entry): 8 values (6 gradient sums, loss term, mask count) in 9 shuffles; 8 lanes store the totals.
@@ -133,8 +143,7 @@ __device__ __forceinline__ void reduce_store_partial(const float (&acc)[PSTRIDE]
 template <int N, int PP>
 __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
                                           const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
-                                          int lx, int ly0, int W, int H, float ddelx_dx, float ddely_dy,
-                                          float* __restrict__ part_out, int lane)
+                                          int lx, int ly0, int W, int H, float* __restrict__ part_out, int lane)
 {
     // The loss term is accumulated on every step although only the last one reports it: a second instantiation without it
     // (one register less per entry) measured 10 % SLOWER overall (more spills in the merged kernel, larger I-cache footprint).
@@ -142,25 +151,17 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
     // chains (ILP), share the per-Gaussian shared-memory loads and accumulate into the same per-entry sums.
     constexpr int NPASS = TILE / 2 / PP;
     int gid[N], goff[N], gw2[N];
-    unsigned grange[N], vrange[N];
-    const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
+    unsigned gmask = 0u;                                           // bit (8u + pass): the lane's pixel of that pass lies in patch u
 #pragma unroll
     for (int u = 0; u < N; u++) {
         const int g = list[u];
         gid[u] = g;
-        {   // passes whose two rows can intersect the Gaussian's alpha >= 1/255 band (warp-uniform, conservative)
-            const float gy = sp.geoA[g].y, ey = sp.geoB[g].w;
-            const float flo = ceilf((gy - ey - (float)ty0 - 1.0f) * 0.5f), fhi = floorf((gy + ey - (float)ty0) * 0.5f);
-            const int vlo = (int)fmaxf(flo, 0.0f), vhi = (int)fminf(fhi, (float)(TILE / 2 - 1));
-            vrange[u] = SSB_VCULL ? ((vhi >= vlo) ? ((unsigned)vlo | ((unsigned)(vhi - vlo + 1) << 8)) : 0u) : (unsigned)((TILE / 2) << 8);
-        }
         const int4 roi = roi_v[g];
         const int rx = lx - roi.x, ry0 = ly0 - roi.y;
         int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                 // first pass with ry0 + 2*pass >= 0
         int phi = (roi.w - ry0 + 1) >> 1;                          // first pass with ry0 + 2*pass >= h
         phi = phi > TILE / 2 ? TILE / 2 : phi;
-        if (!((unsigned)rx < (unsigned)roi.z) || phi <= plo) { plo = 0; phi = 0; }
-        grange[u] = (unsigned)plo | ((unsigned)(phi - plo) << 8);
+        if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
         goff[u] = roi_rel_v[g] + ry0 * roi.z + rx;
         gw2[u] = 2 * roi.z;
     }
@@ -171,19 +172,18 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
         for (int q = 0; q < PSTRIDE; q++) accv[u][q] = 0.f;
     if (lx < W) {
         const float pxf = (float)lx;
-        for (int pass0 = 0; pass0 < NPASS; pass0++) {
-            if (ly0 + 2 * pass0 >= H) break;
+        const int npass = min(NPASS, (H - ly0 + 1) >> 1);       // passes whose first row is inside the image
+        for (int pass0 = 0; pass0 < npass; pass0++) {
             // GT values of the listed Gaussians' channels at the lane's pixels: issued first, consumed only in the backward
             // replay, so the L2 latency hides behind the forward math (a pixel outside a patch reads nothing and gets 0)
             float gtv[PP][N];
+            const unsigned gm = gmask >> pass0;
 #pragma unroll
             for (int q = 0; q < PP; q++) {
-                const int pass = pass0 + q * NPASS;
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if ((unsigned)(pass - (int)(grange[u] & 255u)) < (grange[u] >> 8) && (unsigned)(pass - (int)(vrange[u] & 255u)) < (vrange[u] >> 8))
-                        gtv[q][u] = __ldg(roi_base + goff[u] + pass * gw2[u]);
+                    if (gm & (1u << (8 * u + q * NPASS))) gtv[q][u] = __ldg(roi_base + goff[u] + (pass0 + q * NPASS) * gw2[u]);
                 }
             }
             float pyf[PP];
@@ -206,7 +206,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int q = 0; q < PP; q++) {
                     al[q][u] = 0.f; Gv[q][u] = 0.f; Tb[q][u] = 0.f;
-                    if (!done[q] && (unsigned)(pass0 + q * NPASS - (int)(vrange[u] & 255u)) < (vrange[u] >> 8)) {
+                    if (!done[q]) {
                         float dx, dy, G, alpha;
                         if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf[q], dx, dy, G, alpha)) {
                             const float test_T = __fmul_rn(T[q], __fsub_rn(1.0f, alpha));
@@ -224,20 +224,20 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
             for (int u = N - 1; u >= 0; u--) {
                 if (ok & ((1u << u) | (PP == 2 ? (1u << (N + u)) : 0u))) {
-                    const float4 A = sp.geoA[gid[u]], B = sp.geoB[gid[u]];
-                    const float dx = __fsub_rn(A.x, pxf);
+                    const float2 mxy = *reinterpret_cast<const float2*>(&sp.geoA[gid[u]]);
+                    const float dx = __fsub_rn(mxy.x, pxf);
 #pragma unroll
                     for (int q = 0; q < PP; q++) {
                         if ((ok >> (q * N + u)) & 1u) {
-                            const float dy = __fsub_rn(A.y, pyf[q]);
+                            const float dy = __fsub_rn(mxy.y, pyf[q]);
                             const float gt = gtv[q][u];
-                            const float err = al[q][u] * Tb[q][u] - gt;   // rendered value of channel g minus GT
-                            const float gpix = 2.f * err;                  // unscaled dL/drender (x 1/N later)
-                            S[q] = last_alpha[q] * last_g[q] + (1.f - last_alpha[q]) * S[q];
-                            last_g[q] = gpix; last_alpha[q] = al[q][u];
+                            const float err = fmaf(al[q][u], Tb[q][u], -gt);    // rendered value of channel g minus GT
+                            S[q] = fmaf(last_alpha[q], last_g[q] - S[q], S[q]);  // S <- a_last g_last + (1 - a_last) S
+                            last_g[q] = err; last_alpha[q] = al[q][u];
+                            const float gpos = fmaxf(gt, 0.f);
                             accv[u][7] += (gt > 0.f) ? 0.f : 1.f;          // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
-                            accv[u][6] += (gt > 0.f) ? (err * err - gt * gt) : (err * err);
-                            pair_backward(accv[u], A, B, dx, dy, Gv[q][u], Tb[q][u], gpix, S[q], ddelx_dx, ddely_dy);
+                            accv[u][6] = fmaf(-gpos, gpos, fmaf(err, err, accv[u][6]));   // err^2 - [gt > 0] gt^2
+                            pair_backward(accv[u], dx, dy, Gv[q][u], Tb[q][u], err, S[q]);
                         }
                     }
                 }
@@ -361,11 +361,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                              p.cfg.antialiasing != 0);
             SlotSplats& sp = s_sp[k];
             sp.geoA[j] = make_float4(s.px, s.py, s.opac, 0.f);
-            // rows farther than ey from the centre cannot reach alpha >= 1/255: max_dx power = -0.5 dy^2 det/conx >= -5.55
-            // (same bound as pair_alpha's early-out; opacity <= 1 here) -- +1 px of slack for rounding
-            const float cdet = s.conx * s.conz - s.cony * s.cony;
-            const float ey = (cdet > 0.f && s.conx > 0.f) ? sqrtf(11.1f * s.conx / cdet) + 1.0f : 1e9f;
-            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, ey);
+            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, 0.f);
             sp.depth_bits[j] = __float_as_uint(s.depth);
             sp.rx0[j] = (uint16_t)s.rect.x0; sp.ry0[j] = (uint16_t)s.rect.y0; sp.rx1[j] = (uint16_t)s.rect.x1; sp.ry1[j] = (uint16_t)s.rect.y1;
             sp.tiles[j] = (uint16_t)min(s.tiles, 65535u);
@@ -465,7 +461,6 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             int total = 0;
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) total += s_nact[k];
-            const bool want_loss = (step == p.n_steps - 1);
             const float* roi_base = p.roi_data + s_roi_base;
             for (;;) {
                 int item = 0;
@@ -483,10 +478,9 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const int n = e1 - e0;
                 const SlotSplats& sp = s_sp[k];
                 const uint16_t* list = d_list + (size_t)k * RCAP + e0;
-                const float ddelx_dx = s_halfW[v], ddely_dy = s_halfH[v];
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
-#define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, ddelx_dx, ddely_dy, part_out, lane);
+#define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
                 if (n == 1) SSB_TILE_FAST(1, SSB_PP_N1)
                 else if (n == 2) SSB_TILE_FAST(2, SSB_PP_N2)
                 else if (n == 3) SSB_TILE_FAST(3, 1)
@@ -530,16 +524,16 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                 float gt = 0.f;
                                 if ((unsigned)rx < (unsigned)roi.z && (unsigned)ry < (unsigned)roi.w)
                                     gt = __ldg(roi_base + s_roi_rel[v][g] + ry * roi.z + rx);
-                                const float err = alpha * T - gt;
-                                const float gpix = 2.f * err;
-                                S = last_alpha * last_g + (1.f - last_alpha) * S;
-                                last_g = gpix; last_alpha = alpha;
+                                const float err = fmaf(alpha, T, -gt);
+                                S = fmaf(last_alpha, last_g - S, S);
+                                last_g = err; last_alpha = alpha;
                                 const int u = e - c0;
                                 if (u >= 0 && u < FAST) {
                                     float w[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                    const float gpos = fmaxf(gt, 0.f);
                                     w[7] = (gt > 0.f) ? 0.f : 1.f;
-                                    if (want_loss) w[6] = (gt > 0.f) ? (err * err - gt * gt) : (err * err);
-                                    pair_backward(w, A, B, dx, dy, G, T, gpix, S, ddelx_dx, ddely_dy);
+                                    w[6] = fmaf(-gpos, gpos, err * err);
+                                    pair_backward(w, dx, dy, G, T, err, S);
 #pragma unroll
                                     for (int uu = 0; uu < FAST; uu++)
                                         if (u == uu) {
@@ -587,8 +581,10 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gop = 0.f;
             if (sp.tiles[j] > 0) {
                 float s6[NPART];
+                const float4 gA = sp.geoA[j], gB = sp.geoB[j];
+                records_to_grads(s8, gA.z, gB.x, gB.y, gB.z, s_halfW[v], s_halfH[v], s6);
 #pragma unroll
-                for (int q = 0; q < NPART; q++) s6[q] = s8[q] * invN;
+                for (int q = 0; q < NPART; q++) s6[q] *= invN;
                 const SplatGrad sg = gaussian_backward(
                     s_xyz[3 * j], s_xyz[3 * j + 1], s_xyz[3 * j + 2], &s_cov3d[6 * j], true,
                     s_act_scale[3 * j], s_act_scale[3 * j + 1], s_act_scale[3 * j + 2], 1.0f,
