@@ -1,4 +1,4 @@
-"""Developer tool: time launch-shape variants of the fused optimiser (threads/CTA x min CTAs/SM x r_capacity)."""
+"""Developer tool: A/B-time compile-time variants (-D defines) of the fused optimiser; prints fps, checksum, MPJPE."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 
@@ -22,30 +22,42 @@ x = ps.xyz.cpu().numpy()
 print(json.dumps({"ms": min(ts), "fps": F / min(ts) * 1e3, "checksum": float(np.abs(x).sum()), "mpjpe": trainer.mpjpe(x, gt)}))
 ''' % ROOT
 
-def main():
+def variants_from_argv():
+    """--variants "A=1,B=2;A=0" -> [("A=1","B=2"), ("A=0",)]; default: the library's defaults, twice (run-to-run noise)."""
+    for i, a in enumerate(sys.argv):
+        if a == "--variants":
+            return [tuple(d for d in v.split(",") if d) for v in sys.argv[i + 1].split(";")]
+    return [(), ()]
+
+
+def lib_path(i):
+    return os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{i}.so")
+
+
+def build_variants(variants):
     from skelsplat_b200 import build
-    variants = [(0, 0), (1, 0), (0, 1), (1, 1)]      # (SSB_VCULL, repeat)
-    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512)]
+    for i, defs in enumerate(variants):
+        build.build(force=True, defines=defs, out=lib_path(i))
+
+
+def main(variants):
+    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512), ("panoptic", 1024, 1024)]
     out = {}
-    for thr, cta in variants:
-        lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
-        if not os.path.exists(lib):
-            build.build(force=True, defines=(f"SSB_VCULL={thr}",), out=lib)
     for name, F, rcap in works:
-        for thr, cta in variants:
-            lib = os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so")
-            env = dict(os.environ, SKELSPLAT_B200_LIB=lib)
+        for i, defs in enumerate(variants):
+            env = dict(os.environ, SKELSPLAT_B200_LIB=lib_path(i))
             r = subprocess.run([sys.executable, "-c", CHILD, name, str(F), str(rcap)], env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
-            print(name, F, "rcap", rcap, "threads", thr, "minCTAs", cta, line, flush=True)
-            out[f"{name}|{rcap}|{thr}|{cta}"] = line
+            print(name, F, "rcap", rcap, ",".join(defs) or "default", line, flush=True)
+            out[f"{name}|{rcap}|{i}|{','.join(defs)}"] = line
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tune_opt.json"), "w"), indent=1)
 
+
 if __name__ == "__main__":
-    if "--build-only" in sys.argv:
-        from skelsplat_b200 import build
-        for thr, cta in [(0, 0), (1, 0), (0, 1), (1, 1)]:
-            build.build(force=True, defines=(f"SSB_VCULL={thr}",),
-                        out=os.path.join(ROOT, "skelsplat_b200", "_lib", f"libvariant_{thr}_{cta}.so"))
+    v = variants_from_argv()
+    if "--build-only" in sys.argv:      # here (no GPU): cross-compile the variants so they travel with the snapshot
+        build_variants(v)
     else:
-        main()
+        if not all(os.path.exists(lib_path(i)) for i in range(len(v))):
+            build_variants(v)
+        main(v)

@@ -41,8 +41,18 @@ constexpr int OPT_WARPS = OPT_THREADS / 32;
 #ifndef SSB_PP_N2
 #define SSB_PP_N2 1
 #endif
-// (Tried and removed: exact vertical-band culling of (pass, entry) work -- bitwise-identical results but 8 % slower, the
-//  range tests and their registers cost more than the skipped rows save)
+#ifndef SSB_ROWCULL          // exact row-band culling as warp-uniform pass-loop bounds (0: all 8 passes; bitwise-identical results).
+#define SSB_ROWCULL 1        // An earlier per-(pass, entry) predicate form of the same test measured 8 % SLOWER and was dropped.
+#endif
+#ifndef SSB_PHASE_TIMING     // developer build: per-phase SM cycles of every CTA's thread 0 summed into g_phase_cycles
+#define SSB_PHASE_TIMING 0
+#endif
+#if SSB_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define SSB_PHASE_MARK(i) { if (tid == 0) { const long long t_now = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_now - t_phase)); t_phase = t_now; } }
+#else
+#define SSB_PHASE_MARK(i)
+#endif
 constexpr int MAXJ = 20;
 constexpr int MAXV = 8;
 constexpr int MAX_SLOTS = 4;
@@ -147,22 +157,33 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 {
     // The loss term is accumulated on every step although only the last one reports it: a second instantiation without it
     // (one register less per entry) measured 10 % SLOWER overall (more spills in the merged kernel, larger I-cache footprint).
-    // PP pixels per lane and loop trip (rows pass and pass + 4 when PP == 2): the two pixels are independent dependency
+    // PP pixels per lane and loop trip (two consecutive passes when PP == 2): the two pixels are independent dependency
     // chains (ILP), share the per-Gaussian shared-memory loads and accumulate into the same per-entry sums.
-    constexpr int NPASS = TILE / 2 / PP;
-    int gid[N], goff[N], gw2[N];
+    // Row culling: a pass (= two pixel rows of the tile) is run only if it can intersect the alpha >= 1/255 row band
+    // [rlo, rhi] of at least one listed Gaussian (phase A; exact, see there).  The test is a warp-uniform LOOP BOUND, not a
+    // per-pass predicate -- the per-pass form cost more than it saved.  ~37 % of the (pass, entry) pairs at H36M scale
+    // contain no contributing pixel at all.
+    int gid[N], gw2[N];
+    const float* gptr[N];                                          // the lane's column in row ly0 of patch u (may lie outside it)
     unsigned gmask = 0u;                                           // bit (8u + pass): the lane's pixel of that pass lies in patch u
+    const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
+    int vlo = TILE / 2, vhi = -1;
 #pragma unroll
     for (int u = 0; u < N; u++) {
         const int g = list[u];
         gid[u] = g;
+        if (SSB_ROWCULL) {
+            vlo = min(vlo, (__float_as_int(sp.geoA[g].w) - ty0) >> 1);        // first pass with ty0 + 2 pass + 1 >= rlo
+            vhi = max(vhi, (__float_as_int(sp.geoB[g].w) - ty0) >> 1);        // last pass with ty0 + 2 pass <= rhi
+        }
         const int4 roi = roi_v[g];
         const int rx = lx - roi.x, ry0 = ly0 - roi.y;
         int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                 // first pass with ry0 + 2*pass >= 0
         int phi = (roi.w - ry0 + 1) >> 1;                          // first pass with ry0 + 2*pass >= h
         phi = phi > TILE / 2 ? TILE / 2 : phi;
         if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
-        goff[u] = roi_rel_v[g] + ry0 * roi.z + rx;
+        gptr[u] = roi_base + (roi_rel_v[g] + ry0 * roi.z + rx);
+        asm volatile("" : "+l"(gptr[u]));   // keep the finished 64-bit pointer (else base + offset is re-derived per load)
         gw2[u] = 2 * roi.z;
     }
     float accv[N][PSTRIDE];
@@ -172,8 +193,10 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
         for (int q = 0; q < PSTRIDE; q++) accv[u][q] = 0.f;
     if (lx < W) {
         const float pxf = (float)lx;
-        const int npass = min(NPASS, (H - ly0 + 1) >> 1);       // passes whose first row is inside the image
-        for (int pass0 = 0; pass0 < npass; pass0++) {
+        if (!SSB_ROWCULL) { vlo = 0; vhi = TILE / 2 - 1; }
+        vlo = max(vlo, 0);
+        vhi = min(vhi, min(TILE / 2 - 1, (H - 1 - ty0) >> 1));   // and the pass's first row inside the image
+        for (int pass0 = vlo; pass0 <= vhi; pass0 += PP) {
             // GT values of the listed Gaussians' channels at the lane's pixels: issued first, consumed only in the backward
             // replay, so the L2 latency hides behind the forward math (a pixel outside a patch reads nothing and gets 0)
             float gtv[PP][N];
@@ -183,16 +206,16 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if (gm & (1u << (8 * u + q * NPASS))) gtv[q][u] = __ldg(roi_base + goff[u] + (pass0 + q * NPASS) * gw2[u]);
+                    if (gm & (1u << (8 * u + q))) gtv[q][u] = __ldg(gptr[u] + (pass0 + q) * gw2[u]);
                 }
             }
             float pyf[PP];
             bool live[PP];
 #pragma unroll
             for (int q = 0; q < PP; q++) {
-                const int py = ly0 + 2 * (pass0 + q * NPASS);
+                const int py = ly0 + 2 * (pass0 + q);
                 pyf[q] = (float)py;
-                live[q] = py < H;
+                live[q] = (py < H) && (q == 0 || pass0 + q <= vhi);
             }
             float al[PP][N], Gv[PP][N], Tb[PP][N], T[PP];
             unsigned ok = 0u;                                       // bit (q*N + u)
@@ -209,9 +232,13 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
                     if (!done[q]) {
                         float dx, dy, G, alpha;
                         if (pair_alpha(A.x, A.y, B.x, B.y, B.z, A.z, pxf, pyf[q], dx, dy, G, alpha)) {
-                            const float test_T = __fmul_rn(T[q], __fsub_rn(1.0f, alpha));
-                            if (test_T < T_EPS) done[q] = true;
-                            else { al[q][u] = alpha; Gv[q][u] = G; Tb[q][u] = T[q]; ok |= 1u << (q * N + u); T[q] = test_T; }
+                            if (u == 0) {       // T == 1: test_T = 1 - alpha >= 0.01 can never fall below T_EPS
+                                al[q][u] = alpha; Gv[q][u] = G; Tb[q][u] = 1.0f; ok |= 1u << (q * N + u); T[q] = __fsub_rn(1.0f, alpha);
+                            } else {
+                                const float test_T = __fmul_rn(T[q], __fsub_rn(1.0f, alpha));
+                                if (test_T < T_EPS) done[q] = true;
+                                else { al[q][u] = alpha; Gv[q][u] = G; Tb[q][u] = T[q]; ok |= 1u << (q * N + u); T[q] = test_T; }
+                            }
                         }
                     }
                 }
@@ -246,6 +273,66 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
     }
 #pragma unroll
     for (int u = 0; u < N; u++) reduce_store_partial(accv[u], part_out + (size_t)u * PSTRIDE, lane);
+}
+
+// A tile whose list holds ONE Gaussian (46 % of all (tile, Gaussian) entries at H36M scale).  The transmittance before it is 1
+// and 1 - alpha >= 0.01 > T_EPS, so nothing of the generic bookkeeping (done flags, T, the recurrence S) exists: forward and
+// backward of a pixel collapse into one predicated block -- ~45 instead of ~75 instructions per pixel.  Bit-identical to
+// tile_fast<1, PP> (same operations on the same operands, the dropped ones are multiplications by 1 and additions of 0).
+template <int PP>
+__device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4 roi, int roi_rel, const float* __restrict__ roi_base,
+                                         int lx, int ly0, int W, int H, float* __restrict__ part_out, int lane)
+{
+    const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
+    const float4 A = sp.geoA[g], B = sp.geoB[g];
+    const int vlo = SSB_ROWCULL ? max((__float_as_int(A.w) - ty0) >> 1, 0) : 0;
+    const int vhi = min(SSB_ROWCULL ? ((__float_as_int(B.w) - ty0) >> 1) : TILE / 2 - 1, min(TILE / 2 - 1, (H - 1 - ty0) >> 1));
+    const int rx = lx - roi.x, ry0 = ly0 - roi.y;
+    int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                     // first pass with ry0 + 2*pass >= 0
+    int phi = (roi.w - ry0 + 1) >> 1;                              // first pass with ry0 + 2*pass >= h
+    phi = phi > TILE / 2 ? TILE / 2 : phi;
+    unsigned gmask = 0u;                                           // bit pass: the lane's pixel of that pass lies in the patch
+    if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask = ((1u << (phi - plo)) - 1u) << plo;
+    const float* gp = roi_base + (roi_rel + ry0 * roi.z + rx);     // only dereferenced under gmask
+    asm volatile("" : "+l"(gp));    // keep the finished 64-bit pointer: otherwise base + offset is re-derived for every load (6 instr.)
+    const int gw2 = 2 * roi.z;
+    float acc[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lx < W) {
+        const float dx = __fsub_rn(A.x, (float)lx);
+        const float dxcx = __fmul_rn(dx, B.x), dxcy = __fmul_rn(dx, B.y);      // pass-invariant factors of pair_alpha's power
+        for (int pass0 = vlo; pass0 <= vhi; pass0 += PP) {
+            float gtv[PP];
+#pragma unroll
+            for (int q = 0; q < PP; q++) {
+                gtv[q] = 0.f;
+                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = __ldg(gp + (pass0 + q) * gw2);
+            }
+#pragma unroll
+            for (int q = 0; q < PP; q++) {
+                const int py = ly0 + 2 * (pass0 + q);
+                if (py < H && (q == 0 || pass0 + q <= vhi)) {
+                    // pair_alpha (forward.cu:352-364), same operation order
+                    const float dy = __fsub_rn(A.y, (float)py);
+                    float t = __fmul_rn(dy, __fmul_rn(dy, B.z));
+                    t = __fmaf_rn(dx, dxcx, t);
+                    const float power = __fmaf_rn(t, -0.5f, -__fmul_rn(dy, dxcy));
+                    if (!(power > 0.0f) && !(power < -5.55f && A.z <= 1.0f)) {
+                        const float G = expf(power);
+                        const float alpha = fminf(ALPHA_MAX, __fmul_rn(A.z, G));
+                        if (!(alpha < ALPHA_MIN)) {
+                            const float gt = gtv[q];
+                            const float err = alpha - gt;                  // rendered value of channel g minus GT
+                            const float gpos = fmaxf(gt, 0.f);
+                            acc[7] += (gt > 0.f) ? 0.f : 1.f;
+                            acc[6] = fmaf(-gpos, gpos, fmaf(err, err, acc[6]));
+                            pair_backward(acc, dx, dy, G, 1.0f, err, 0.0f);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    reduce_store_partial(acc, part_out, lane);
 }
 
 // NT threads per CTA: 512 with two CTAs per SM, or 1024 with one when the binning state (r_capacity) is too large for two.
@@ -332,7 +419,11 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     const int acc = p.cfg.accumulation_steps;     // == SLOTS (host guarantees)
     float last_loss = 0.f;
 
+#if SSB_PHASE_TIMING
+    long long t_phase = clock64();
+#endif
     for (int step = 0; step < p.n_steps; step++) {
+        SSB_PHASE_MARK(7)
         // ============ phase A: activations + projection of every (slot, joint) ============
         if (tid < J) {
             const int j = tid;
@@ -360,13 +451,21 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                              s_view[v], s_proj[v], s_W[v], s_H[v], s_tfx[v], s_tfy[v], s_fx[v], s_fy[v],
                                              p.cfg.antialiasing != 0);
             SlotSplats& sp = s_sp[k];
-            sp.geoA[j] = make_float4(s.px, s.py, s.opac, 0.f);
-            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, 0.f);
+            // Row band outside which the Gaussian cannot reach alpha >= 1/255 (so contributes nothing, forward.cu:358-363):
+            // max over dx of power(dx, dy) = -0.5 dy^2 det/conx must be >= -5.55 (pair_alpha's exact early-out; opacity <= 1)
+            // => |dy| <= sqrt(11.1 conx/det), widened by 1 % + 1 px against fp32 rounding of the conic.  A near-singular
+            // conic (det lost to cancellation) gets no band.
+            const float cdet = s.conx * s.conz - s.cony * s.cony;
+            const float ey = (s.conx > 0.f && cdet > 1e-4f * s.conx * s.conz) ? 1.01f * sqrtf(11.1f * s.conx / cdet) + 1.0f : 1e9f;
+            const int rlo = (int)fminf(fmaxf(ceilf(s.py - ey), 0.0f), 65535.0f), rhi = (int)fminf(fmaxf(floorf(s.py + ey), -1.0f), 65535.0f);
+            sp.geoA[j] = make_float4(s.px, s.py, s.opac, __int_as_float(rlo));
+            sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, __int_as_float(rhi));
             sp.depth_bits[j] = __float_as_uint(s.depth);
             sp.rx0[j] = (uint16_t)s.rect.x0; sp.ry0[j] = (uint16_t)s.rect.y0; sp.rx1[j] = (uint16_t)s.rect.x1; sp.ry1[j] = (uint16_t)s.rect.y1;
             sp.tiles[j] = (uint16_t)min(s.tiles, 65535u);
         }
         __syncthreads();
+        SSB_PHASE_MARK(0)
         // ============ phase B: binning (scan, keys, sort, tile runs) per slot ============
         if (tid < SLOTS) {
             SlotSplats& sp = s_sp[tid];
@@ -412,6 +511,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             }
         }
         __syncthreads();
+        SSB_PHASE_MARK(1)
         // bitonic sort of all slots at once (independent sub-arrays of length nsort)
         for (int kk = 2; kk <= nsort; kk <<= 1) {
             for (int jj = kk >> 1; jj > 0; jj >>= 1) {
@@ -426,6 +526,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 __syncthreads();
             }
         }
+        SSB_PHASE_MARK(2)
         for (int i = tid; i < SLOTS * nsort; i += NT) {
             const int k = i >> lgsort, e = i & (nsort - 1);
             if (e < s_R[k]) {
@@ -455,6 +556,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         }
         __syncthreads();
 
+        SSB_PHASE_MARK(3)
         // ============ phase C: tiles.  One warp per active tile, handed out dynamically (tile lists differ in length);
         // every result is a per-(tile,Gaussian) record, so the schedule does not influence any sum ============
         {
@@ -481,7 +583,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
 #define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
-                if (n == 1) SSB_TILE_FAST(1, SSB_PP_N1)
+                if (n == 1) { const int g1 = list[0]; tile_one<SSB_PP_N1>(sp, g1, s_roi[v][g1], s_roi_rel[v][g1], roi_base, lx, ly0, W, H, part_out, lane); }
                 else if (n == 2) SSB_TILE_FAST(2, SSB_PP_N2)
                 else if (n == 3) SSB_TILE_FAST(3, 1)
                 else if (n == 4) SSB_TILE_FAST(4, 1)
@@ -552,6 +654,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         }
         __syncthreads();
 
+        SSB_PHASE_MARK(4)
         // ============ phase D: per-Gaussian backward chain + gradient bookkeeping ============
         // D1: fixed-order (emission order) sum of each Gaussian's per-tile records
         float s8[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -647,6 +750,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             }
         }
         __syncthreads();
+        SSB_PHASE_MARK(5)
         // ============ phase E: Adam (torch.optim.Adam, foreach path; train.py:215-222) ============
         if (tid < J * 11) {
             const int i = tid;
@@ -669,6 +773,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         __syncthreads();
     }
 
+    SSB_PHASE_MARK(6)
     // ---------------- write back ----------------
     for (int i = tid; i < J * 3; i += NT) { p.xyz[(size_t)frame * J * 3 + i] = s_xyz[i]; p.scaling_raw[(size_t)frame * J * 3 + i] = s_scal[i]; }
     for (int i = tid; i < J * 4; i += NT) p.rotation_raw[(size_t)frame * J * 4 + i] = s_rot[i];
@@ -686,6 +791,15 @@ static size_t opt_dyn_smem(int slots, int rcap) {
 using namespace ssb;
 
 extern "C" {
+
+#if SSB_PHASE_TIMING
+// developer build only: cycles per phase (A, B keys, B sort, B lists, C tiles, D chain, E Adam + tail, loop head)
+int ssb_debug_phase_cycles(unsigned long long* out8, int reset) {
+    if (cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 8) != cudaSuccess) return SSB_ERR_CUDA;
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+    return SSB_OK;
+}
+#endif
 
 size_t ssb_optimize_workspace_bytes(const ssb_opt_config* cfg, int n_frames) {
     (void)cfg;

@@ -115,6 +115,12 @@ def pack_sequence(cfg: SceneConfig, cams, poses_init, poses_2d, device="cuda", h
 
 
 def make_opt_config(cfg: SceneConfig, r_capacity=256, iterations=None):
+    if cfg.loss_function != "l2_gaussian":
+        # train.py:150 unpacks `l2_loss, error = opt_criterion(...)`; l2_gaussian is the only entry of the reference's
+        # loss table that returns that tuple (utils/loss_utils.py:86-100), i.e. the only one its training loop can run.
+        # The other losses stay available on the dense surface (skelsplat_b200.loss_utils / ssb_loss_forward).
+        raise NotImplementedError(f"fused optimiser implements loss_function='l2_gaussian' (got {cfg.loss_function!r}); "
+                                  "use skelsplat_b200.training.optimise_frame_dropin for the dense losses")
     oc = _L.OptConfig()
     oc.J, oc.V = cfg.n_joints, cfg.nviews
     oc.iterations = cfg.iterations if iterations is None else iterations

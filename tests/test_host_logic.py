@@ -143,3 +143,13 @@ def test_synthetic_sequences_are_seeded_and_shaped():
         (l0, l1), (r0, r1) = cfg.limb_pairs[0], cfg.limb_pairs[1]
         gt = a.frames[0].pose_3d_gt
         assert math.isclose(np.linalg.norm(gt[l0] - gt[l1]), np.linalg.norm(gt[r0] - gt[r1]), rel_tol=1e-9)
+
+
+def test_fused_path_rejects_losses_the_reference_loop_cannot_run():
+    """train.py:150 unpacks a (loss, error) tuple, which only l2_gaussian returns: the fused optimiser implements that loss
+    and refuses the others loudly instead of silently optimising a different objective."""
+    import dataclasses
+    bad = dataclasses.replace(configs.H36M, loss_function="l1_gaussian")
+    with pytest.raises(NotImplementedError):
+        trainer.make_opt_config(bad)
+    assert trainer.make_opt_config(configs.H36M).J == 17
