@@ -4,7 +4,7 @@
 import ctypes as C, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 LIB = os.path.join(ROOT, "skelsplat_b200", "_lib", "libvariant_phase.so")
-NAMES = ["A activations+projection", "B scan/rank/keys", "B bitonic sort", "B lists+compaction", "C tiles", "D chain",
+NAMES = ["A activations+projection", "B scan/rank/placement", "(unused)", "B tile-run compaction", "C tiles", "D chain",
          "tail", "E Adam"]
 
 if "--build-only" in sys.argv:

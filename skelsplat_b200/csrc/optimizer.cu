@@ -31,7 +31,6 @@ namespace ssb {
 #define SSB_OPT_THREADS 512
 #endif
 constexpr int OPT_THREADS = SSB_OPT_THREADS;
-constexpr int OPT_WARPS = OPT_THREADS / 32;
 #ifndef SSB_OPT_MIN_CTAS
 #define SSB_OPT_MIN_CTAS 2
 #endif
@@ -105,9 +104,9 @@ struct SlotSplats {
     float4 geoA[MAXJ];                     // px, py, opacity, -
     float4 geoB[MAXJ];                     // conic x, y, z, -
     uint32_t depth_bits[MAXJ];
-    uint16_t rx0[MAXJ], ry0[MAXJ], rx1[MAXJ], ry1[MAXJ];
+    uint2 rectp[MAXJ];                     // tile rect: x0 | y0 << 16, x1 | y1 << 16 (exclusive); all zero when no tile is touched
     uint16_t tiles[MAXJ], offs[MAXJ];      // tiles touched, inclusive scan
-    uint8_t rank[MAXJ], of_rank[MAXJ];     // depth rank of each Gaussian ((depth bits, id) order) and its inverse
+    uint8_t rank[MAXJ];                    // depth rank of each Gaussian in (depth bits, id) order
 };
 
 // Per (pixel, Gaussian) backward terms (backward.cu:600-636), accumulated as RAW moment sums: with
@@ -137,6 +136,29 @@ __device__ __forceinline__ void records_to_grads(const float (&r)[PSTRIDE], floa
     out[3] = -opac * r[3];
     out[4] = -opac * r[4];
     out[5] = 2.f * r[5];
+}
+
+// pair_alpha (common.cuh; forward.cu:352-364) with the pass-invariant factors dx, dx*conx, dx*cony supplied by the caller:
+// the same operations in the same order, hence the same bits.
+__device__ __forceinline__ bool pair_alpha_hoisted(float gpy, float conz, float opac, float dx, float dxcx, float dxcy, float pyf,
+                                                   float& dy, float& G, float& alpha) {
+    dy = __fsub_rn(gpy, pyf);
+    float t = __fmul_rn(dy, __fmul_rn(dy, conz));
+    t = __fmaf_rn(dx, dxcx, t);
+    const float power = __fmaf_rn(t, -0.5f, -__fmul_rn(dy, dxcy));
+    if (power > 0.0f) return false;
+    if (power < -5.55f && opac <= 1.0f) return false;
+    G = expf(power);
+    alpha = fminf(ALPHA_MAX, __fmul_rn(opac, G));
+    return !(alpha < ALPHA_MIN);
+}
+
+// Loss-mask count, loss term and raw moment sums of one contributing (pixel, Gaussian) pair.
+__device__ __forceinline__ void pair_accumulate(float (&acc)[PSTRIDE], float dx, float dy, float G, float Tb, float err, float S, float gt) {
+    const float gpos = fmaxf(gt, 0.f);
+    acc[7] += (gt > 0.f) ? 0.f : 1.f;                              // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
+    acc[6] = fmaf(-gpos, gpos, fmaf(err, err, acc[6]));            // err^2 - [gt > 0] gt^2
+    pair_backward(acc, dx, dy, G, Tb, err, S);
 }
 
 // One reduction per (tile, entry): 8 values (6 gradient sums, loss term, mask count) in 9 shuffles; 8 lanes store the totals.
@@ -261,10 +283,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
                             const float err = fmaf(al[q][u], Tb[q][u], -gt);    // rendered value of channel g minus GT
                             S[q] = fmaf(last_alpha[q], last_g[q] - S[q], S[q]);  // S <- a_last g_last + (1 - a_last) S
                             last_g[q] = err; last_alpha[q] = al[q][u];
-                            const float gpos = fmaxf(gt, 0.f);
-                            accv[u][7] += (gt > 0.f) ? 0.f : 1.f;          // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
-                            accv[u][6] = fmaf(-gpos, gpos, fmaf(err, err, accv[u][6]));   // err^2 - [gt > 0] gt^2
-                            pair_backward(accv[u], dx, dy, Gv[q][u], Tb[q][u], err, S[q]);
+                            pair_accumulate(accv[u], dx, dy, Gv[q][u], Tb[q][u], err, S[q], gt);
                         }
                     }
                 }
@@ -320,12 +339,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
                         const float G = expf(power);
                         const float alpha = fminf(ALPHA_MAX, __fmul_rn(A.z, G));
                         if (!(alpha < ALPHA_MIN)) {
-                            const float gt = gtv[q];
-                            const float err = alpha - gt;                  // rendered value of channel g minus GT
-                            const float gpos = fmaxf(gt, 0.f);
-                            acc[7] += (gt > 0.f) ? 0.f : 1.f;
-                            acc[6] = fmaf(-gpos, gpos, fmaf(err, err, acc[6]));
-                            pair_backward(acc, dx, dy, G, 1.0f, err, 0.0f);
+                            pair_accumulate(acc, dx, dy, G, 1.0f, alpha - gtv[q], 0.0f, gtv[q]);   // err = rendered - GT
                         }
                     }
                 }
@@ -333,6 +347,72 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
         }
     }
     reduce_store_partial(acc, part_out, lane);
+}
+
+// A tile whose list holds TWO Gaussians (38 % of the entries at H36M scale): written out without the generic bookkeeping.
+// Front Gaussian 0 sees T = 1 (never terminates the pixel); Gaussian 1 sees T1 = 1 - alpha0 and may hit the T < 1e-4 stop; the
+// recurrence reduces to S = alpha1 * err1 for Gaussian 0.  Per-entry constants live in registers for the whole tile.
+// Bit-identical to tile_fast<2, 1>.
+__device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
+                                         const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
+                                         int lx, int ly0, int W, int H, float* __restrict__ part_out, int lane)
+{
+    const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
+    const int g0 = list[0], g1 = list[1];
+    const float4 A0 = sp.geoA[g0], B0 = sp.geoB[g0], A1 = sp.geoA[g1], B1 = sp.geoB[g1];
+    int vlo = 0, vhi = TILE / 2 - 1;
+    if (SSB_ROWCULL) {
+        vlo = max(min(__float_as_int(A0.w), __float_as_int(A1.w)) - ty0 >> 1, 0);
+        vhi = min(max(__float_as_int(B0.w), __float_as_int(B1.w)) - ty0 >> 1, TILE / 2 - 1);
+    }
+    vhi = min(vhi, (H - 1 - ty0) >> 1);
+    const float* gptr[2];
+    int gw2[2];
+    unsigned gmask = 0u;                                           // bit (8u + pass): the lane's pixel of that pass lies in patch u
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int g = u ? g1 : g0;
+        const int4 roi = roi_v[g];
+        const int rx = lx - roi.x, ry0 = ly0 - roi.y;
+        int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;
+        int phi = (roi.w - ry0 + 1) >> 1;
+        phi = phi > TILE / 2 ? TILE / 2 : phi;
+        if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
+        gptr[u] = roi_base + (roi_rel_v[g] + ry0 * roi.z + rx);
+        asm volatile("" : "+l"(gptr[u]));
+        gw2[u] = 2 * roi.z;
+    }
+    float acc0[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc1[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lx < W) {
+        const float pxf = (float)lx;
+        const float dx0 = __fsub_rn(A0.x, pxf), dx1 = __fsub_rn(A1.x, pxf);
+        const float dxcx0 = __fmul_rn(dx0, B0.x), dxcy0 = __fmul_rn(dx0, B0.y);
+        const float dxcx1 = __fmul_rn(dx1, B1.x), dxcy1 = __fmul_rn(dx1, B1.y);
+        for (int pass = vlo; pass <= vhi; pass++) {
+            const unsigned gm = gmask >> pass;
+            float gt0 = 0.f, gt1 = 0.f;
+            if (gm & 1u) gt0 = __ldg(gptr[0] + pass * gw2[0]);
+            if (gm & 0x100u) gt1 = __ldg(gptr[1] + pass * gw2[1]);
+            const int py = ly0 + 2 * pass;
+            if (py < H) {
+                const float pyf = (float)py;
+                float dy0, G0, a0, dy1, G1, a1;
+                const bool v0 = pair_alpha_hoisted(A0.y, B0.z, A0.z, dx0, dxcx0, dxcy0, pyf, dy0, G0, a0);
+                const float T1 = v0 ? __fsub_rn(1.0f, a0) : 1.0f;             // 1 - alpha0 >= 0.01: Gaussian 0 never stops the pixel
+                bool v1 = pair_alpha_hoisted(A1.y, B1.z, A1.z, dx1, dxcx1, dxcy1, pyf, dy1, G1, a1);
+                if (v1 && __fmul_rn(T1, __fsub_rn(1.0f, a1)) < T_EPS) v1 = false;  // forward.cu:366-371: the pixel is done
+                float S = 0.f;
+                if (v1) {
+                    const float err1 = fmaf(a1, T1, -gt1);
+                    pair_accumulate(acc1, dx1, dy1, G1, T1, err1, 0.f, gt1);
+                    S = a1 * err1;
+                }
+                if (v0) pair_accumulate(acc0, dx0, dy0, G0, 1.0f, a0 - gt0, S, gt0);
+            }
+        }
+    }
+    reduce_store_partial(acc0, part_out, lane);
+    reduce_store_partial(acc1, part_out + PSTRIDE, lane);
 }
 
 // NT threads per CTA: 512 with two CTAs per SM, or 1024 with one when the binning state (r_capacity) is too large for two.
@@ -461,18 +541,33 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             sp.geoA[j] = make_float4(s.px, s.py, s.opac, __int_as_float(rlo));
             sp.geoB[j] = make_float4(s.conx, s.cony, s.conz, __int_as_float(rhi));
             sp.depth_bits[j] = __float_as_uint(s.depth);
-            sp.rx0[j] = (uint16_t)s.rect.x0; sp.ry0[j] = (uint16_t)s.rect.y0; sp.rx1[j] = (uint16_t)s.rect.x1; sp.ry1[j] = (uint16_t)s.rect.y1;
+            sp.rectp[j] = s.tiles > 0 ? make_uint2((uint32_t)s.rect.x0 | ((uint32_t)s.rect.y0 << 16), (uint32_t)s.rect.x1 | ((uint32_t)s.rect.y1 << 16))
+                                      : make_uint2(0u, 0u);
             sp.tiles[j] = (uint16_t)min(s.tiles, 65535u);
         }
         __syncthreads();
         SSB_PHASE_MARK(0)
-        // ============ phase B: binning (scan, keys, sort, tile runs) per slot ============
+        // ============ phase B: binning per slot.  The reference sorts (tile | depth) keys (rasterizer_impl.cu:303-311); with at
+        // most MAXJ Gaussians whose tiles form rectangles, the sorted position of an entry has a closed form:
+        //   pos(j, tile t) = sum over j' of #{tiles of rect(j') that precede t in row-major order}
+        //                  + #{j' : t in rect(j') and (depth, id)(j') < (depth, id)(j)}
+        // i.e. the order of the stable sort, without sorting: no compare-exchange network, no barriers (the bitonic sort this
+        // replaces was 36 barrier-separated stages = 6 % of the kernel).  Entries are handled one per thread. ============
         if (tid < SLOTS) {
             SlotSplats& sp = s_sp[tid];
             uint32_t a = 0;
             for (int j = 0; j < J; j++) { a += sp.tiles[j]; sp.offs[j] = (uint16_t)min(a, 65535u); }
-            if (a > (uint32_t)RCAP) { s_status |= (int)SSB_STATUS_R_OVERFLOW; a = RCAP; }
+            // capacity overflow: flag the frame (the host re-runs it with a larger r_capacity) and skip the slot
+            if (a > (uint32_t)RCAP) { s_status |= (int)SSB_STATUS_R_OVERFLOW; a = 0; }
             s_R[tid] = (int)a;
+        }
+        if (tid >= 32 && tid < 32 + SLOTS * J) {      // depth rank: position of (depth bits, id) among the slot's Gaussians
+            const int k = (tid - 32) / J, j = (tid - 32) % J;
+            SlotSplats& sp = s_sp[k];
+            const uint32_t dj = sp.depth_bits[j];
+            int r = 0;
+            for (int o = 0; o < J; o++) { const uint32_t d = sp.depth_bits[o]; r += (d < dj || (d == dj && o < j)) ? 1 : 0; }
+            sp.rank[j] = (uint8_t)r;
         }
         __syncthreads();
         int nsort = 32, lgsort = 5;
@@ -482,72 +577,48 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             for (int k = 0; k < SLOTS; k++) Rmax = max(Rmax, s_R[k]);
             while (nsort < Rmax) { nsort <<= 1; lgsort++; }       // RCAP is a power of two >= Rmax
         }
-        // 32-bit sort words: tile (17 bits) | depth rank of the Gaussian (5) | emission index (10).  (tile, rank) is unique per
-        // entry, so sorting the words reproduces the reference's stable (tile | depth bits) order; the emission index rides along.
-        for (int i = tid; i < SLOTS * nsort; i += NT) SSB_KEYS32(i >> lgsort)[i & (nsort - 1)] = 0xFFFFFFFFu;
-        if (tid < SLOTS * J) {      // depth rank: position of (depth bits, id) among the slot's Gaussians
-            const int k = tid / J, j = tid % J;
-            SlotSplats& sp = s_sp[k];
-            const uint32_t dj = sp.depth_bits[j];
-            int r = 0;
-            for (int o = 0; o < J; o++) { const uint32_t d = sp.depth_bits[o]; r += (d < dj || (d == dj && o < j)) ? 1 : 0; }
-            sp.rank[j] = (uint8_t)r;
-            sp.of_rank[r] = (uint8_t)j;
-        }
-        __syncthreads();
-        if (tid < SLOTS * J) {
-            const int k = tid / J, j = tid % J;
-            const SlotSplats& sp = s_sp[k];
-            if (sp.tiles[j] > 0) {
-                const int v = (step * acc + k) % V;
-                const uint32_t gx = (uint32_t)((s_W[v] + TILE - 1) / TILE);
-                uint32_t off = (j == 0) ? 0u : sp.offs[j - 1];
-                const uint32_t low = ((uint32_t)sp.rank[j] << 10);
-                for (uint32_t y = sp.ry0[j]; y < sp.ry1[j]; y++)
-                    for (uint32_t x = sp.rx0[j]; x < sp.rx1[j]; x++) {
-                        if (off < (uint32_t)s_R[k]) SSB_KEYS32(k)[off] = ((y * gx + x) << 15) | low | off;
-                        off++;
+        for (int i = tid; i < SLOTS * nsort; i += NT) {
+            const int k = i >> lgsort, idx = i & (nsort - 1);      // idx: emission index (Gaussian-major, row-major in its rect)
+            if (idx < s_R[k]) {
+                const SlotSplats& sp = s_sp[k];
+                int j = 0;
+                while ((int)sp.offs[j] <= idx) j++;
+                const int local = idx - (j ? (int)sp.offs[j - 1] : 0);
+                const uint2 rj = sp.rectp[j];
+                const int x0 = (int)(rj.x & 0xFFFFu), y0 = (int)(rj.x >> 16), wj = (int)(rj.y & 0xFFFFu) - x0;
+                const int yy = local / wj;
+                const int y = y0 + yy, x = x0 + (local - yy * wj);
+                const int rank_j = sp.rank[j];
+                int pos = 0;
+                for (int o = 0; o < J; o++) {
+                    const uint2 ro = sp.rectp[o];                  // empty (0,0,0,0) for a Gaussian that touches no tile
+                    const int ox0 = (int)(ro.x & 0xFFFFu), oy0 = (int)(ro.x >> 16), ox1 = (int)(ro.y & 0xFFFFu), oy1 = (int)(ro.y >> 16);
+                    const int ow = ox1 - ox0;
+                    pos += min(max(y - oy0, 0), oy1 - oy0) * ow;               // whole rows above y
+                    if (y >= oy0 && y < oy1) {
+                        pos += min(max(x - ox0, 0), ow);                       // same row, left of x
+                        if (x >= ox0 && x < ox1 && (int)sp.rank[o] < rank_j) pos++;   // same tile, nearer Gaussian
                     }
+                }
+                SSB_KEYS32(k)[pos] = ((uint32_t)y << 8) | (uint32_t)x;         // packed tile coordinate of sorted entry pos
+                d_list[(size_t)k * RCAP + pos] = (uint16_t)j;
+                d_inv[(size_t)k * RCAP + idx] = (uint16_t)pos;
             }
         }
         __syncthreads();
         SSB_PHASE_MARK(1)
-        // bitonic sort of all slots at once (independent sub-arrays of length nsort)
-        for (int kk = 2; kk <= nsort; kk <<= 1) {
-            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                for (int i = tid; i < SLOTS * (nsort >> 1); i += NT) {
-                    // i enumerates the compare-exchange pairs: insert a 0 bit at position log2(jj)
-                    const int k = i >> (lgsort - 1), q = i & ((nsort >> 1) - 1);
-                    const int e = ((q & ~(jj - 1)) << 1) | (q & (jj - 1));
-                    uint32_t* K = SSB_KEYS32(k);
-                    const uint32_t ka = K[e], kb = K[e | jj];
-                    if ((ka > kb) == ((e & kk) == 0)) { K[e] = kb; K[e | jj] = ka; }
-                }
-                __syncthreads();
-            }
-        }
-        SSB_PHASE_MARK(2)
-        for (int i = tid; i < SLOTS * nsort; i += NT) {
-            const int k = i >> lgsort, e = i & (nsort - 1);
-            if (e < s_R[k]) {
-                const uint32_t key = SSB_KEYS32(k)[e];
-                d_list[(size_t)k * RCAP + e] = (uint16_t)s_sp[k].of_rank[(key >> 10) & 31u];
-                d_inv[(size_t)k * RCAP + (key & 1023u)] = (uint16_t)e;
-            }
-        }
         if (warp < SLOTS) {      // warp k: ordered compaction of the tile runs of slot k
             const int k = warp, R = s_R[k];
-            const uint32_t gxk = (uint32_t)((s_W[s_slot_view[k]] + TILE - 1) / TILE);
             const uint32_t* K = SSB_KEYS32(k);
             int nact = 0;
             for (int base = 0; base < R; base += 32) {
                 const int i = base + lane;
                 bool start = false; uint32_t tile = 0;
-                if (i < R) { tile = K[i] >> 15; start = (i == 0) || ((K[i - 1] >> 15) != tile); }
+                if (i < R) { tile = K[i]; start = (i == 0) || (K[i - 1] != tile); }
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, start);
                 if (start) {
                     const int a = nact + __popc(m & ((1u << lane) - 1u));
-                    d_tile[(size_t)k * RCAP + a] = (uint16_t)(((tile / gxk) << 8) | (tile % gxk));
+                    d_tile[(size_t)k * RCAP + a] = (uint16_t)tile;
                     d_start[(size_t)k * RCAP + a] = (uint16_t)i;
                 }
                 nact += __popc(m);
@@ -584,7 +655,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
 #define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
                 if (n == 1) { const int g1 = list[0]; tile_one<SSB_PP_N1>(sp, g1, s_roi[v][g1], s_roi_rel[v][g1], roi_base, lx, ly0, W, H, part_out, lane); }
-                else if (n == 2) SSB_TILE_FAST(2, SSB_PP_N2)
+                else if (n == 2) tile_two(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
                 else if (n == 3) SSB_TILE_FAST(3, 1)
                 else if (n == 4) SSB_TILE_FAST(4, 1)
 #undef SSB_TILE_FAST
@@ -793,7 +864,7 @@ using namespace ssb;
 extern "C" {
 
 #if SSB_PHASE_TIMING
-// developer build only: cycles per phase (A, B keys, B sort, B lists, C tiles, D chain, E Adam + tail, loop head)
+// developer build only: cycles per phase (A, B placement, -, B compaction, C tiles, D chain, tail, E Adam)
 int ssb_debug_phase_cycles(unsigned long long* out8, int reset) {
     if (cudaMemcpyFromSymbol(out8, g_phase_cycles, sizeof(unsigned long long) * 8) != cudaSuccess) return SSB_ERR_CUDA;
     if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
