@@ -27,7 +27,7 @@ extern "C" {
 #define SSB_ERR_UNSUPPORTED -4
 
 /* Device-side status bits written into a view's state header (see ssb_state_header). */
-#define SSB_STATUS_R_OVERFLOW 1u /* more (Gaussian,tile) pairs than r_capacity: list truncated */
+#define SSB_STATUS_R_OVERFLOW 1u /* more (Gaussian,tile) pairs than r_capacity: result invalid, re-run with more */
 
 int         ssb_version(void);
 const char* ssb_error_string(int code);
@@ -173,7 +173,7 @@ typedef struct ssb_opt_config {
     int   limb_pairs[8];
     float lr_scaling, lr_rotation, lr_opacity;
     float beta1, beta2, eps;    /* 0.9, 0.999, 1e-15 */
-    int   r_capacity;           /* max (Gaussian,tile) pairs per view (<= 1024) */
+    int   r_capacity;           /* max (Gaussian,tile) pairs per view: a multiple of 32, 32..1024 */
     int   antialiasing;
 } ssb_opt_config;
 

@@ -16,7 +16,12 @@ ts = []
 for rep in range(3):
     for d, s_ in zip((ps.xyz, ps.scaling, ps.rotation, ps.opacity), init): d.copy_(s_)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); trainer.optimize_packed(ps, r_capacity=rcap, check=(rep == 0)); e1.record(); torch.cuda.synchronize()
+    e0.record()
+    try:
+        trainer.optimize_packed(ps, r_capacity=rcap, check=(rep == 0))
+    except Exception as exc:      # capacity overflow with an explicit r_capacity: report how many frames
+        print(json.dumps({"error": str(exc)[:160]})); sys.exit(0)
+    e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 x = ps.xyz.cpu().numpy()
 print(json.dumps({"ms": min(ts), "fps": F / min(ts) * 1e3, "checksum": float(np.abs(x).sum()), "mpjpe": trainer.mpjpe(x, gt)}))
@@ -26,7 +31,7 @@ def variants_from_argv():
     """--variants "A=1,B=2;A=0" -> [("A=1","B=2"), ("A=0",)]; default: the library's defaults, twice (run-to-run noise)."""
     for i, a in enumerate(sys.argv):
         if a == "--variants":
-            return [tuple(d for d in v.split(",") if d) for v in sys.argv[i + 1].split(";")]
+            return [tuple(d for d in v.split(",") if d) for v in sys.argv[i + 1].split(";")]   # "...@192": r_capacity override
     return [(), ()]
 
 
@@ -37,7 +42,7 @@ def lib_path(i):
 def build_variants(variants):
     from skelsplat_b200 import build
     for i, defs in enumerate(variants):
-        build.build(force=True, defines=defs, out=lib_path(i))
+        build.build(force=True, defines=tuple(d.split("@")[0] for d in defs if d.split("@")[0]), out=lib_path(i))
 
 
 def main(variants):
@@ -46,6 +51,9 @@ def main(variants):
     for name, F, rcap in works:
         for i, defs in enumerate(variants):
             env = dict(os.environ, SKELSPLAT_B200_LIB=lib_path(i))
+            over = [d.split("@")[1] for d in defs if "@" in d]
+            if over and name == "h36m":
+                rcap = int(over[0])
             r = subprocess.run([sys.executable, "-c", CHILD, name, str(F), str(rcap)], env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
             print(name, F, "rcap", rcap, ",".join(defs) or "default", line, flush=True)

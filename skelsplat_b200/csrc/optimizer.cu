@@ -575,7 +575,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             int Rmax = 0;
 #pragma unroll
             for (int k = 0; k < SLOTS; k++) Rmax = max(Rmax, s_R[k]);
-            while (nsort < Rmax) { nsort <<= 1; lgsort++; }       // RCAP is a power of two >= Rmax
+            while (nsort < Rmax) { nsort <<= 1; lgsort++; }       // power of two >= every slot's R: thread -> (slot, entry) split
         }
         for (int i = tid; i < SLOTS * nsort; i += NT) {
             const int k = i >> lgsort, idx = i & (nsort - 1);      // idx: emission index (Gaussian-major, row-major in its rect)
@@ -885,7 +885,7 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
     if (!cfg || !cams || !lr_xyz_host || n_frames < 0) return SSB_ERR_INVALID;
     if (cfg->J <= 0 || cfg->J > MAXJ || cfg->V <= 0 || cfg->V > MAXV || cams->n_views != cfg->V) return SSB_ERR_UNSUPPORTED;
     if (cfg->accumulation_steps < 1 || cfg->accumulation_steps > MAX_SLOTS || cfg->accumulation_steps == 3) return SSB_ERR_UNSUPPORTED;
-    if (cfg->r_capacity < 32 || cfg->r_capacity > 1024 || (cfg->r_capacity & (cfg->r_capacity - 1))) return SSB_ERR_CAPACITY;
+    if (cfg->r_capacity < 32 || cfg->r_capacity > 1024 || (cfg->r_capacity % 32)) return SSB_ERR_CAPACITY;
     const int n_steps = cfg->iterations / cfg->accumulation_steps;   // trailing iterations never reach an optimiser step
     if (n_steps > MAX_STEPS) return SSB_ERR_CAPACITY;
     for (int i = 0; i < 8; i++) if (cfg->limb_pairs[i] < 0 || cfg->limb_pairs[i] >= cfg->J) return SSB_ERR_INVALID;
@@ -915,7 +915,7 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
     const int slots = cfg->accumulation_steps;
     const size_t smem = opt_dyn_smem(slots, cfg->r_capacity);
     // two 512-thread CTAs per SM when their shared memory fits (227 KB/SM), else one 1024-thread CTA: 32 warps/SM either way
-    const bool big = (2 * (smem + 17 * 1024) > 227 * 1024);
+    const bool big = (SSB_OPT_MIN_CTAS * (smem + 17 * 1024) > 227 * 1024);
 #define SSB_LAUNCH_OPT(S)                                                                                         \
     {                                                                                                             \
         if (big) {                                                                                                \

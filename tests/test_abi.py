@@ -76,7 +76,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert L.ssb_loss_forward(C.c_int(0), C.c_int64(10), None, None, None, None, None) == -1
     assert L.ssb_fused_ssim_forward(C.c_int(1), C.c_int(1), C.c_int(8), C.c_int(8), C.c_float(1e-4), C.c_float(9e-4), None, None, None, None, None, None, None) == -1
     oc = lib.OptConfig()
-    oc.J, oc.V, oc.iterations, oc.accumulation_steps, oc.r_capacity = 17, 4, 500, 4, 300   # not a power of two
+    oc.J, oc.V, oc.iterations, oc.accumulation_steps, oc.r_capacity = 17, 4, 500, 4, 300   # not a multiple of 32
     lr = (C.c_double * 501)()
     assert L.ssb_optimize_frames(C.byref(oc), C.c_int(1), C.byref(lib.Cameras(4, None, None, None, None, 100, 100, 0.5, 0.5, 0)), lr,
                                  None, None, None, None, None, None, None, None, None, None) == -2
