@@ -441,7 +441,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ int s_ngt[MAXV];            // sum_j #{gt > 0}
     __shared__ float s_sgt2[MAXV];         // sum_j sum gt^2
     __shared__ SlotSplats s_sp[SLOTS];
-    __shared__ int s_R[SLOTS], s_nact[SLOTS], s_next;
+    __shared__ int s_R[SLOTS], s_nact[SLOTS], s_next[SLOTS];
     __shared__ float s_jcnt[SLOTS][MAXJ], s_jloss[SLOTS][MAXJ];
     __shared__ float s_lsum[SLOTS][NW];
     __shared__ int s_status;
@@ -522,7 +522,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             for (int k = 0; k < 6; k++) s_cov3d[6 * j + k] = cov[k];
         }
         if (tid < SLOTS) s_slot_view[tid] = (step * acc + tid) % V;
-        if (tid == 0) s_next = 0;
+        if (tid < SLOTS) s_next[tid] = 0;
         __syncthreads();
         if (tid < SLOTS * J) {
             const int k = tid / J, j = tid % J;
@@ -631,25 +631,24 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         // ============ phase C: tiles.  One warp per active tile, handed out dynamically (tile lists differ in length);
         // every result is a per-(tile,Gaussian) record, so the schedule does not influence any sum ============
         {
-            int total = 0;
-#pragma unroll
-            for (int k = 0; k < SLOTS; k++) total += s_nact[k];
             const float* roi_base = p.roi_data + s_roi_base;
+            // one counter per slot; a warp starts on slot (warp mod SLOTS) and moves on when that slot's tiles are handed out,
+            // so everything that depends on the slot only (view, image size, splat table) is loaded once per slot, not per tile
+            for (int kk = 0; kk < SLOTS; kk++) {
+            const int k = (warp + kk) & (SLOTS - 1);
+            const int nact = s_nact[k];
+            const int v = s_slot_view[k];
+            const int W = s_W[v], H = s_H[v];
+            const SlotSplats& sp = s_sp[k];
             for (;;) {
-                int item = 0;
-                if (lane == 0) item = atomicAdd(&s_next, 1);
-                item = __shfl_sync(0xFFFFFFFFu, item, 0);
-                if (item >= total) break;
-                int k = 0, a = item;
-#pragma unroll
-                for (int kk = 0; kk < SLOTS - 1; kk++) { if (k == kk && a >= s_nact[kk]) { a -= s_nact[kk]; k = kk + 1; } }
-                const int v = s_slot_view[k];
-                const int W = s_W[v], H = s_H[v];
+                int a = 0;
+                if (lane == 0) a = atomicAdd(&s_next[k], 1);
+                a = __shfl_sync(0xFFFFFFFFu, a, 0);
+                if (a >= nact) break;
                 const int tile = d_tile[(size_t)k * RCAP + a];                 // packed (ty << 8) | tx
                 const int e0 = d_start[(size_t)k * RCAP + a];
-                const int e1 = (a + 1 < s_nact[k]) ? (int)d_start[(size_t)k * RCAP + a + 1] : s_R[k];
+                const int e1 = (a + 1 < nact) ? (int)d_start[(size_t)k * RCAP + a + 1] : s_R[k];
                 const int n = e1 - e0;
-                const SlotSplats& sp = s_sp[k];
                 const uint16_t* list = d_list + (size_t)k * RCAP + e0;
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
@@ -721,6 +720,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                             if (c0 + u < n) reduce_store_partial(accv[u], part_out + (size_t)(c0 + u) * PSTRIDE, lane);   // warp-uniform
                     }
                 }
+            }
             }
         }
         __syncthreads();
