@@ -32,44 +32,88 @@ N_DISTINCT = 64          # distinct synthetic frames generated on the host; repl
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML (what nvidia-smi
+    reads) is polled from a thread every 20 ms -- an `nvidia-smi -lms` child needs ~1 s to start on an 8-GPU box, longer
+    than a short timed region -- with the nvidia-smi loop as fallback.  start() before the warm-up, begin() when the timed
+    region starts, stop() after it: only samples inside [begin, stop] are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index=0):
-        self.samples, self.proc, self.gpu_index = [], None, gpu_index
+        self.samples, self.proc, self.gpu_index = [], None, gpu_index        # (t, sm_mhz, max_mhz, [reasons])
+        self.mode, self.t0, self._stop = None, None, threading.Event()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip()]
+        if ids and all(x.strip().isdigit() for x in ids) and self.gpu_index < len(ids):
+            return int(ids[self.gpu_index])
+        return self.gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        bits = int(get_reasons(h))
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx,
+                                             [n for n, b in self.REASON_BITS.items() if bits & b]))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.02)
+            self.mode = "nvml"
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.proc, self.mode = None, None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                self.samples.append((time.perf_counter(), float(f[1]), float(f[2]),
+                                     [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                                      if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def stop(self):
+        t1 = time.perf_counter()
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        window = "timed region"
+        if not inside:                       # region shorter than one sampling period: nearest samples under the same load
+            inside, window = [x for x in self.samples if x[0] <= t1][-3:], "warm-up (timed region shorter than the sampling period)"
+        sm = [x[1] for x in inside]
+        reasons = sorted({r for x in inside for r in x[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(x[2] for x in inside) if inside else None,
+                "reasons": reasons, "samples": len(sm), "source": self.mode, "window": window}
 
 
 # ----------------------------------------------------------------------------------------- data
@@ -88,6 +132,7 @@ def make_host_batch(cfg, F, seed):
     out["roi_offset"] = np.ascontiguousarray(np.concatenate([host["roi_offset"] + r * per for r in range(reps)])[:F])
     out["roi_data"] = np.ascontiguousarray(np.concatenate([host["roi_data"]] * reps))
     gt = np.concatenate([np.stack([f.pose_3d_gt for f in seq.frames])] * reps)[:F]
+    out["poses_2d"] = np.ascontiguousarray(np.concatenate([poses_2d.astype(np.float32)] * reps)[:F])   # detections (e2e input)
     return seq, out, gt
 
 
@@ -114,7 +159,9 @@ def run_ours(args):
     cfg = configs.H36M
     F = args.frames
     seq, host, gt = make_host_batch(cfg, F, seed=100 + rank)      # each rank optimises its own shard of the sequence
+    det_host = {"poses_2d": torch.from_numpy(host.pop("poses_2d")).pin_memory()}
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    det_host["xyz"] = pinned["xyz"]
     ps = trainer.pack_sequence(cfg, seq.cameras, host["xyz"], None, dev, host=host)
     init = tuple(t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity))
     gathered = torch.empty((world * F, cfg.n_joints, 3), dtype=torch.float32, device=dev) if world > 1 else None
@@ -133,29 +180,39 @@ def run_ours(args):
 
     # e2e: the public streaming API -- every step copies that step's inputs from pinned host memory and reads the poses back;
     # the copy of step i+1 overlaps the optimisation of step i (double-buffered)
-    so = trainer.StreamingOptimizer(cfg, seq.cameras, F, int(pinned["roi_data"].numel()), dev)
+    # Two forms: (1) detections in -> poses out (the e2e headline): a step's host inputs are what a user of the reference has
+    # on the host -- 2D detections + the initial 3D guess -- and the GT heatmap ROIs are generated on the GPU inside the timed
+    # region (the reference also builds its heatmaps on the GPU from the detections, utils/general_utils.py:175-304);
+    # (2) ROI streaming: host-prepared heatmap patches cross PCIe every step (841 MB/step), reported as e2e_roi_streaming.
+    so = trainer.StreamingOptimizer(cfg, seq.cameras, F, int(pinned["roi_data"].numel() * 1.1), dev)
     tickets = []
 
-    def step_e2e():
-        tickets.append(so.submit(pinned))
-        launches[0] += 1
-        if len(tickets) >= 2:
-            so.result(tickets[-2])                      # poses of the previous batch are on the host before the next submit
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, so.slots[tickets[-1] % 2]["ps"].xyz)
+    def make_step_e2e(submit, arg):
+        def step():
+            tickets.append(submit(arg))
+            launches[0] += 1
+            if len(tickets) >= 2:
+                so.result(tickets[-2])                  # poses of the previous batch are on the host before the next submit
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, so.slots[tickets[-1] % 2]["ps"].xyz)
+        return step
+    step_e2e = make_step_e2e(so.submit_detections, det_host)
+    step_e2e_roi = make_step_e2e(so.submit, pinned)
 
     def timed(fn, steps, warmup, sample_clocks=False, streams=()):
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = launches[0]
+        if sampler:
+            sampler.begin()
         e0.record()
         for st in streams:                                   # side streams start after e0 ...
             st.wait_stream(torch.cuda.current_stream())
@@ -183,13 +240,17 @@ def run_ours(args):
     k0.record(); trainer.optimize_packed(ps, check=False); k1.record(); torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1)
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, streams=(so.copy_stream, so.compute_stream))
+    final_e2e = so.result(tickets[-1])
+    del tickets[:]
+    ms_e2e_roi, _, _ = timed(step_e2e_roi, args.steps, args.warmup, streams=(so.copy_stream, so.compute_stream))
     so.result(tickets[-1])
     final = ps.xyz.cpu().numpy()
 
     total_frames = world * F
     value = total_frames * args.steps / (ms / 1e3)
     e2e_value = total_frames * args.steps / (ms_e2e / 1e3)
-    h2d = sum(int(v.numel() * v.element_size()) for v in pinned.values())
+    h2d = sum(int(v.numel() * v.element_size()) for v in det_host.values())
+    h2d_roi = sum(int(v.numel() * v.element_size()) for v in pinned.values())
     d2h = int(F * cfg.n_joints * 3 * 4 + F * 4)          # final poses + per-frame status words
 
     if rank != 0:
@@ -245,7 +306,13 @@ def run_ours(args):
                    "loss": "l2_gaussian + 1e-5 limb consistency", "parallelism": f"frame-sharded x{world}" + (", NCCL all_gather of final poses" if world > 1 else ""),
                    "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "includes": "trainer.StreamingOptimizer: per step pinned-host -> device copy of initial poses/params + GT heatmap ROIs, fused optimiser, device -> host copy of final poses + status; copies of step i+1 overlap the kernel of step i"},
+                "ms_per_step": round(ms_e2e / args.steps, 3), "mpjpe_mm": round(trainer.mpjpe(final_e2e, gt), 3),
+                "includes": "trainer.StreamingOptimizer.submit_detections: per step pinned-host -> device copy of the 2D detections + initial 3D guess, "
+                            "initial Gaussian state and GT heatmap ROIs generated on the GPU (ssb_heatmap_roi_*), fused optimiser, device -> host copy "
+                            "of final poses + status words; the copies of step i+1 overlap the kernels of step i"},
+        "e2e_roi_streaming": {"value": round(total_frames * args.steps / (ms_e2e_roi / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_roi,
+                              "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e_roi / args.steps, 3),
+                              "includes": "trainer.StreamingOptimizer.submit: host-prepared GT heatmap ROI patches + initial state cross PCIe every step"},
         "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "setup_gpu": setup, "dense_surface": dense_ctx, "cpu_baseline": cpu,
         "accuracy": {"mpjpe_init_mm": round(mpjpe(host["xyz"], gt), 3), "mpjpe_final_mm": round(mpjpe(final, gt), 3)},
     }
@@ -436,6 +503,7 @@ def run_reference(args):
     sampler = ClockSampler(0)
     if use_ref:
         sampler.start()
+        sampler.begin()
     secs = [one(f) for f in seq.frames[args.warmup:args.warmup + args.steps]]
     clocks = sampler.stop() if use_ref else None
     per_frame = float(np.sum(secs)) / len(secs) * (cfg.iterations / iters)

@@ -28,6 +28,8 @@ extern "C" {
 
 /* Device-side status bits written into a view's state header (see ssb_state_header). */
 #define SSB_STATUS_R_OVERFLOW 1u /* more (Gaussian,tile) pairs than r_capacity: result invalid, re-run with more */
+#define SSB_STATUS_ROI_OVERFLOW 2u /* heatmap patches need more than the roi_data capacity given: patches were skipped */
+#define SSB_STATUS_ROI_TOO_WIDE 4u /* a heatmap patch is wider than 256 px (sigma > 31 px): outside the supported regime */
 
 int         ssb_version(void);
 const char* ssb_error_string(int code);
@@ -206,8 +208,15 @@ int ssb_triangulate_dlt(int n_frames, int V, int J, const double* P, const doubl
 int ssb_heatmap_roi_rects(int n_frames, int J, const ssb_cameras* cams, const float* xyz, const float* scaling_raw,
                           const float* rotation_raw, const float* poses_2d, float scaling_modifier,
                           int* roi_rect, float* roi_sigma, int* roi_center, int64_t* roi_size, void* stream);
+/* Exclusive scan roi_size[n] -> roi_offset[n] on the device (n = F*V*J); *total (device pointer, may be NULL) receives the
+ * packed size.  With it the detections -> ROIs -> optimiser pipeline needs no host round trip. */
+int ssb_heatmap_roi_offsets(int64_t n, const int64_t* roi_size, int64_t* roi_offset, int64_t* total, void* stream);
+/* capacity: number of floats roi_data can hold, or -1 for "exactly sized by the caller".  A patch that does not fit (or is
+ * wider than 256 px) is skipped and SSB_STATUS_ROI_OVERFLOW / SSB_STATUS_ROI_TOO_WIDE is OR-ed into *status (device int,
+ * may be NULL). */
 int ssb_heatmap_roi_fill(int n_frames, int J, const ssb_cameras* cams, const int* roi_rect, const float* roi_sigma,
-                         const int* roi_center, const int64_t* roi_offset, float* roi_data, void* stream);
+                         const int* roi_center, const int64_t* roi_offset, float* roi_data, int64_t capacity, int* status,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -167,7 +167,8 @@ __device__ double reflect_response(int idx, int pos, int n, double sigma, int ra
 // then per-channel min-max normalisation (min == 0: the patch never covers the whole image) with the +1e-8.
 __global__ void __launch_bounds__(128)
 roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __restrict__ roi_sigma, const int* __restrict__ roi_center,
-                const long long* __restrict__ roi_offset, ssb_cameras cams, int V, int J, float* __restrict__ roi_data)
+                const long long* __restrict__ roi_offset, ssb_cameras cams, int V, int J, float* __restrict__ roi_data,
+                long long capacity, int* __restrict__ status)
 {
     const int i = blockIdx.x;
     if (i >= n_patches) return;
@@ -180,7 +181,14 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
     __shared__ float s_col[256];
     __shared__ double s_row[256];
     __shared__ float s_max;
-    if (w > 256 || h > 256) return;            // sigma > 31 px: not a SkelSplat regime (host validates)
+    if (w > 256 || h > 256) {                  // sigma > 31 px: not a SkelSplat regime
+        if (status && threadIdx.x == 0) atomicOr(status, (int)SSB_STATUS_ROI_TOO_WIDE);
+        return;
+    }
+    if (capacity >= 0 && roi_offset[i] + (long long)w * h > capacity) {       // packed buffer too small: nothing is written
+        if (status && threadIdx.x == 0) atomicOr(status, (int)SSB_STATUS_ROI_OVERFLOW);
+        return;
+    }
     double wy = 0.0, wx = 0.0;
     for (int k = -ry; k <= ry; k++) wy += exp(-0.5 / (s1 * s1) * (double)(k * k));
     for (int k = -rx; k <= rx; k++) wx += exp(-0.5 / (s2 * s2) * (double)(k * k));
@@ -200,6 +208,35 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
         const int a = t / w, b = t - a * w;
         dst[t] = (float)((double)s_col[a] * s_row[b]) / denom;
     }
+}
+
+// Exclusive scan of the patch sizes into packed offsets (+ the total), one CTA: n = F*V*J is ~1e5, a few microseconds.
+// Keeps the detections -> ROIs -> optimiser pipeline free of host round trips.
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS)
+roi_offsets_kernel(long long n, const long long* __restrict__ size, long long* __restrict__ offset, long long* __restrict__ total)
+{
+    __shared__ long long s_warp[SCAN_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const long long b = per * tid, e = (b + per < n) ? b + per : n;
+    long long sum = 0;
+    for (long long i = b; i < e; i++) sum += size[i];
+    long long incl = sum;                                          // inclusive scan of the per-thread sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += t; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    long long run = incl - sum + (warp ? s_warp[warp - 1] : 0);
+    for (long long i = b; i < e; i++) { offset[i] = run; run += size[i]; }
+    if (tid == SCAN_THREADS - 1 && total) *total = s_warp[SCAN_THREADS / 32 - 1];
 }
 
 }  // namespace ssb
@@ -231,14 +268,23 @@ int ssb_heatmap_roi_rects(int n_frames, int J, const ssb_cameras* cams, const fl
     return ssb_set_cuda_error(cudaGetLastError());
 }
 
+int ssb_heatmap_roi_offsets(int64_t n, const int64_t* roi_size, int64_t* roi_offset, int64_t* total, void* stream_) {
+    if (n < 0) return SSB_ERR_INVALID;
+    if (n > 0 && (!roi_size || !roi_offset)) return SSB_ERR_INVALID;
+    roi_offsets_kernel<<<1, SCAN_THREADS, 0, (cudaStream_t)stream_>>>((long long)n, (const long long*)roi_size, (long long*)roi_offset,
+                                                                      (long long*)total);
+    return ssb_set_cuda_error(cudaGetLastError());
+}
+
 int ssb_heatmap_roi_fill(int n_frames, int J, const ssb_cameras* cams, const int* roi_rect, const float* roi_sigma,
-                         const int* roi_center, const int64_t* roi_offset, float* roi_data, void* stream_) {
+                         const int* roi_center, const int64_t* roi_offset, float* roi_data, int64_t capacity, int* status,
+                         void* stream_) {
     if (!cams || n_frames < 0 || J <= 0 || cams->n_views <= 0) return SSB_ERR_INVALID;
     if (n_frames == 0) return SSB_OK;
     if (!roi_rect || !roi_sigma || !roi_center || !roi_offset || !roi_data) return SSB_ERR_INVALID;
     const int n = n_frames * cams->n_views * J;
     roi_fill_kernel<<<n, 128, 0, (cudaStream_t)stream_>>>(n, roi_rect, roi_sigma, roi_center, (const long long*)roi_offset, *cams,
-                                                          cams->n_views, J, roi_data);
+                                                          cams->n_views, J, roi_data, (long long)capacity, status);
     return ssb_set_cuda_error(cudaGetLastError());
 }
 

@@ -51,7 +51,7 @@ EXPORTS = [
     "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency",
     "ssb_fused_ssim_forward", "ssb_fused_ssim_backward",
     "ssb_optimize_workspace_bytes", "ssb_optimize_frames",
-    "ssb_triangulate_dlt", "ssb_heatmap_roi_rects", "ssb_heatmap_roi_fill",
+    "ssb_triangulate_dlt", "ssb_heatmap_roi_rects", "ssb_heatmap_roi_offsets", "ssb_heatmap_roi_fill",
 ]
 
 

@@ -247,6 +247,65 @@ class StreamingOptimizer:
         self.compute_stream = torch.cuda.Stream(device=device)
         self.n_submitted = 0
         self.launches = 0
+        self._det = None              # buffers of the detections-in path, created on first use
+
+    # ---- detections in, poses out: initial guess + GT heatmap ROIs are produced on the GPU (setup_gpu), so a step moves
+    # ---- F*V*J*2 detection floats (+ optional initial poses) over PCIe instead of the ROI patches themselves
+    def _det_buffers(self):
+        if self._det is None:
+            F, J, V, dev = self.F, self.cfg.n_joints, self.cfg.nviews, self.device
+            _, scal, rot, opa = initial_raw_state(self.cfg, np.zeros((1, J, 3), np.float32))
+            tmpl = tuple(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a, (F,) + a.shape[1:]))).to(dev) for a in (scal, rot, opa))
+            per = []
+            for _ in range(2):
+                per.append(dict(p2d=torch.empty((F, V, J, 2), dtype=torch.float32, device=dev),
+                                sigma=torch.empty((F, V, J, 2), dtype=torch.float32, device=dev),
+                                center=torch.empty((F, V, J, 2), dtype=torch.int32, device=dev),
+                                size=torch.empty((F, V, J), dtype=torch.int64, device=dev),
+                                setup_status=torch.zeros(1, dtype=torch.int32, device=dev),
+                                setup_status_host=torch.zeros(1, dtype=torch.int32).pin_memory()))
+            self._det = dict(tmpl=tmpl, per=per, P=torch.as_tensor(np.asarray([c.P3x4() for c in self.cams], np.float64)).to(dev))
+        return self._det
+
+    def submit_detections(self, host):
+        """host: dict of PINNED tensors  poses_2d [F,V,J,2] fp32  and optionally  xyz [F,J,3] fp32 (initial guess; without it
+        the DLT triangulation of the detections is used, triangulation.py:122-150).  Returns a ticket for result()."""
+        from . import setup_gpu
+        i = self.n_submitted
+        sl = self.slots[i % 2]
+        if sl["busy"]:
+            sl["done"].synchronize()
+        det = self._det_buffers()
+        d, ps = det["per"][i % 2], sl["ps"]
+        if host["poses_2d"].shape[0] != self.F:
+            raise ValueError("batch does not fit the streaming buffers")
+        with torch.cuda.stream(self.copy_stream):
+            d["p2d"].copy_(host["poses_2d"], non_blocking=True)
+            if host.get("xyz") is not None:
+                ps.xyz.copy_(host["xyz"], non_blocking=True)
+            sl["copied"].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(sl["copied"])
+            if host.get("xyz") is None:
+                ps.xyz.copy_(setup_gpu.triangulate_dlt(det["P"], d["p2d"], self.device))
+            for dst, src in zip((ps.scaling, ps.rotation, ps.opacity), det["tmpl"]):
+                dst.copy_(src)
+            d["setup_status"].zero_()
+            setup_gpu.generate_heatmap_rois_into(self.cfg, ps.viewmatrix, ps.projmatrix, ps.dims, ps.tanfov, ps.Wmax, ps.Hmax,
+                                                 ps.xyz, ps.scaling, ps.rotation, d["p2d"], ps.roi_rect, d["sigma"], d["center"],
+                                                 d["size"], ps.roi_offset, ps.roi_data, d["setup_status"])
+            rcap = default_r_capacity(self.cfg) if self.r_capacity is None else self.r_capacity
+            oc = make_opt_config(self.cfg, rcap, self.iterations)
+            lr = xyz_lr_table(self.cfg, ps.spatial_lr_scale, oc.iterations)
+            status = _launch(ps, oc, lr, sl["loss"])
+            self.launches += 1
+            sl["out"].copy_(ps.xyz, non_blocking=True)
+            sl["status"].copy_(status, non_blocking=True)
+            d["setup_status_host"].copy_(d["setup_status"], non_blocking=True)
+            sl["done"].record(self.compute_stream)
+        sl["host"], sl["busy"], sl["det"] = host, True, d
+        self.n_submitted += 1
+        return i
 
     def submit(self, host):
         i = self.n_submitted
@@ -273,13 +332,25 @@ class StreamingOptimizer:
             sl["out"].copy_(ps.xyz, non_blocking=True)
             sl["status"].copy_(status, non_blocking=True)
             sl["done"].record(self.compute_stream)
-        sl["host"], sl["busy"] = host, True
+        sl["host"], sl["busy"], sl["det"] = host, True, None
         self.n_submitted += 1
         return i
 
     def result(self, ticket):
         sl = self.slots[ticket % 2]
         sl["done"].synchronize()
+        if sl.get("det") is not None:
+            if int(sl["det"]["setup_status_host"][0]) != 0 or int(sl["status"].max()) != 0:
+                # rare: the ROI patches outgrew the streaming buffer, or frames outgrew r_capacity -> exact synchronous
+                # re-run of the batch through the exactly-sized, retrying path
+                from . import setup_gpu
+                host = sl["host"]
+                with torch.cuda.stream(self.compute_stream):
+                    full = setup_gpu.pack_sequence_gpu(self.cfg, self.cams, host["poses_2d"], host.get("xyz"), self.device)
+                    optimize_packed(full, self.iterations, None)
+                    sl["out"].copy_(full.xyz)
+                self.compute_stream.synchronize()
+            return sl["out"].numpy().copy()
         if int(sl["status"].max()) != 0:
             # rare: some frames outgrew r_capacity -> exact synchronous re-run of the batch with the retrying path
             ps = sl["ps"]

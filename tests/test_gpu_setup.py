@@ -61,3 +61,35 @@ def test_whole_gpu_pipeline_detections_to_poses():
     xyz, _ = trainer.optimize_packed(ps)
     ref = trainer.optimize_sequence(seq, DEV)
     assert np.linalg.norm(xyz.cpu().numpy() - ref, axis=-1).max() < 0.05
+
+
+def test_streaming_detections_in_poses_out():
+    """StreamingOptimizer.submit_detections (pinned detections -> GPU DLT / initial state / heatmap ROIs -> fused optimiser ->
+    poses, no host round trip) returns bit-for-bit what the exactly-sized synchronous pipeline returns, with and without
+    host-provided initial poses; a streaming buffer that is too small is detected on the device and the batch is re-run
+    through the synchronous path (same result)."""
+    cfg = configs.H36M
+    F = 6
+    seqs = [synthetic.make_sequence(cfg, F, seed=50 + i) for i in range(3)]
+    cams = seqs[0].cameras
+    hosts, refs = [], []
+    for n, sq in enumerate(seqs):
+        p2 = torch.from_numpy(np.stack([f.poses_2d for f in sq.frames]).astype(np.float32)).pin_memory()
+        h = {"poses_2d": p2}
+        if n == 1:                                                   # this batch brings its own initial guess
+            h["xyz"] = torch.from_numpy(np.stack([f.pose_3d_init for f in sq.frames]).astype(np.float32)).pin_memory()
+        hosts.append(h)
+        ps = setup_gpu.pack_sequence_gpu(cfg, cams, p2, h.get("xyz"), DEV)
+        cap = int(ps.roi_data.numel())
+        refs.append(trainer.optimize_packed(ps, iterations=40)[0].cpu().numpy())
+    so = trainer.StreamingOptimizer(cfg, cams, F, 2 * cap, DEV, iterations=40)
+    t = [so.submit_detections(h) for h in hosts[:2]]
+    outs = [so.result(t[0])]
+    t.append(so.submit_detections(hosts[2]))
+    outs += [so.result(t[1]), so.result(t[2])]
+    for a, b in zip(outs, refs):
+        assert np.array_equal(a, b)
+    assert so.launches == 3
+    small = trainer.StreamingOptimizer(cfg, cams, F, cap // 2, DEV, iterations=40)      # ROI patches do not fit
+    assert np.array_equal(small.result(small.submit_detections(hosts[0])), refs[0])
+    assert int(small.slots[0]["det"]["setup_status_host"][0]) & 2
