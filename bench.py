@@ -191,10 +191,11 @@ def run_ours(args):
         def step():
             tickets.append(submit(arg))
             launches[0] += 1
+            if world > 1:                               # stream-ordered after this batch's optimiser, as in the resident step
+                with torch.cuda.stream(so.compute_stream):
+                    dist.all_gather_into_tensor(gathered, so.slots[tickets[-1] % 2]["ps"].xyz)
             if len(tickets) >= 2:
                 so.result(tickets[-2])                  # poses of the previous batch are on the host before the next submit
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, so.slots[tickets[-1] % 2]["ps"].xyz)
         return step
     step_e2e = make_step_e2e(so.submit_detections, det_host)
     step_e2e_roi = make_step_e2e(so.submit, pinned)
@@ -237,8 +238,15 @@ def run_ours(args):
     # kernel-only duration for the roofline (same stream, CUDA events around the launch alone)
     reset(); torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(); trainer.optimize_packed(ps, check=False); k1.record(); torch.cuda.synchronize()
+    oc_k = trainer.make_opt_config(cfg, trainer.default_r_capacity(cfg))
+    lr_k = trainer.xyz_lr_table(cfg, ps.spatial_lr_scale, oc_k.iterations)
+    loss_k = torch.empty(F, dtype=torch.float32, device=dev)
+    k0.record(); status_k = trainer._launch(ps, oc_k, lr_k, loss_k); k1.record(); torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1)
+    n_over_t = (status_k != 0).sum().to(torch.int64).reshape(1)       # frames that outgrew r_capacity (they need the retry path): must be 0
+    if world > 1:
+        dist.all_reduce(n_over_t)
+    n_overflowed = int(n_over_t.item())
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, streams=(so.copy_stream, so.compute_stream))
     final_e2e = so.result(tickets[-1])
     del tickets[:]
@@ -302,7 +310,7 @@ def run_ours(args):
         "metric": "optimised_frames_per_sec", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "iterations": cfg.iterations, "adam_steps": cfg.iterations // cfg.accumulation_steps,
+        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "r_capacity": trainer.default_r_capacity(cfg), "frames_over_capacity_all_ranks": n_overflowed, "iterations": cfg.iterations, "adam_steps": cfg.iterations // cfg.accumulation_steps,
                    "loss": "l2_gaussian + 1e-5 limb consistency", "parallelism": f"frame-sharded x{world}" + (", NCCL all_gather of final poses" if world > 1 else ""),
                    "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)"},
         "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

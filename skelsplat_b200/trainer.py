@@ -139,7 +139,11 @@ def make_opt_config(cfg: SceneConfig, r_capacity=256, iterations=None):
 def default_r_capacity(cfg: SceneConfig):
     """(Gaussian,tile) pairs per view held in shared memory.  ~10/joint at H36M/OP scale, 25-60/joint at Panoptic scale.
     Small capacities raise occupancy; frames that outgrow the capacity are detected on the device and re-run (below)."""
-    return {"panoptic": 1024, "occlusion-person": 512}.get(cfg.name, 256)
+    if cfg.name.startswith("panoptic"):
+        return 1024
+    if cfg.name.startswith("occlusion-person"):
+        return 512
+    return 320        # H36M: 256 is outgrown by ~1 % of the synthetic frames during optimisation; 320 costs 0.5 % throughput
 
 
 MAX_R_CAPACITY = 1024
@@ -180,24 +184,39 @@ def optimize_packed(ps: PackedSequence, iterations=None, r_capacity=None, final_
     status = _launch(ps, oc, lr, final_loss)
     if check:
         bad = torch.nonzero(status != 0).flatten()
-        while bad.numel():
-            if r_capacity is not None or rcap >= MAX_R_CAPACITY:
+        if bad.numel():
+            if r_capacity is not None:
                 raise _L.SkelSplatLibraryError(f"{bad.numel()} frame(s) exceeded r_capacity={rcap} (Gaussian,tile) pairs per view")
-            rcap *= 2
-            oc = make_opt_config(cfg, rcap, iterations)
-            sub = PackedSequence(cfg=cfg, n_frames=int(bad.numel()), xyz=init[0][bad].contiguous(), scaling=init[1][bad].contiguous(),
-                                 rotation=init[2][bad].contiguous(), opacity=init[3][bad].contiguous(), viewmatrix=ps.viewmatrix,
-                                 projmatrix=ps.projmatrix, dims=ps.dims, tanfov=ps.tanfov, roi_rect=ps.roi_rect[bad].contiguous(),
-                                 roi_offset=ps.roi_offset[bad].contiguous(), roi_data=ps.roi_data, spatial_lr_scale=ps.spatial_lr_scale,
-                                 Wmax=ps.Wmax, Hmax=ps.Hmax)
-            sub_loss = torch.empty(sub.n_frames, dtype=torch.float32, device=ps.xyz.device)
-            sub_status = _launch(sub, oc, lr, sub_loss)
-            good = sub_status == 0
-            idx = bad[good]
-            ps.xyz[idx] = sub.xyz[good]; ps.scaling[idx] = sub.scaling[good]; ps.rotation[idx] = sub.rotation[good]
-            ps.opacity[idx] = sub.opacity[good]; final_loss[idx] = sub_loss[good]
-            bad = bad[~good]
+            retry_overflowed(ps, bad, tuple(t[bad] for t in init), rcap, iterations, final_loss)
     return ps.xyz, final_loss
+
+
+def retry_overflowed(ps: PackedSequence, bad, init_bad, rcap, iterations=None, final_loss=None):
+    """Re-run ONLY the frames ``bad`` (indices into ps) from their initial state ``init_bad`` = (xyz, scaling, rotation, opacity)
+    with the capacity doubled until they fit; results are written into ps in place.  Exact: a frame's result does not depend
+    on the capacity it ran with, nor on the other frames of the launch."""
+    cfg = ps.cfg
+    lr = xyz_lr_table(cfg, ps.spatial_lr_scale, cfg.iterations if iterations is None else iterations)
+    cur = tuple(t.contiguous() for t in init_bad)
+    while bad.numel():
+        if rcap >= MAX_R_CAPACITY:
+            raise _L.SkelSplatLibraryError(f"{bad.numel()} frame(s) exceeded r_capacity={rcap} (Gaussian,tile) pairs per view")
+        rcap = min(2 * rcap, MAX_R_CAPACITY)
+        oc = make_opt_config(cfg, rcap, iterations)
+        sub = PackedSequence(cfg=cfg, n_frames=int(bad.numel()), xyz=cur[0].clone(), scaling=cur[1].clone(), rotation=cur[2].clone(),
+                             opacity=cur[3].clone(), viewmatrix=ps.viewmatrix, projmatrix=ps.projmatrix, dims=ps.dims, tanfov=ps.tanfov,
+                             roi_rect=ps.roi_rect[bad].contiguous(), roi_offset=ps.roi_offset[bad].contiguous(), roi_data=ps.roi_data,
+                             spatial_lr_scale=ps.spatial_lr_scale, Wmax=ps.Wmax, Hmax=ps.Hmax)
+        sub_loss = torch.empty(sub.n_frames, dtype=torch.float32, device=ps.xyz.device)
+        sub_status = _launch(sub, oc, lr, sub_loss)
+        good = sub_status == 0
+        idx = bad[good]
+        ps.xyz[idx] = sub.xyz[good]; ps.scaling[idx] = sub.scaling[good]; ps.rotation[idx] = sub.rotation[good]
+        ps.opacity[idx] = sub.opacity[good]
+        if final_loss is not None:
+            final_loss[idx] = sub_loss[good]
+        bad = bad[~good]
+        cur = tuple(t[~good].contiguous() for t in cur)
 
 
 def optimize_sequence(seq, device="cuda", iterations=None, r_capacity=None):
@@ -339,25 +358,33 @@ class StreamingOptimizer:
     def result(self, ticket):
         sl = self.slots[ticket % 2]
         sl["done"].synchronize()
-        if sl.get("det") is not None:
-            if int(sl["det"]["setup_status_host"][0]) != 0 or int(sl["status"].max()) != 0:
-                # rare: the ROI patches outgrew the streaming buffer, or frames outgrew r_capacity -> exact synchronous
-                # re-run of the batch through the exactly-sized, retrying path
-                from . import setup_gpu
-                host = sl["host"]
-                with torch.cuda.stream(self.compute_stream):
-                    full = setup_gpu.pack_sequence_gpu(self.cfg, self.cams, host["poses_2d"], host.get("xyz"), self.device)
-                    optimize_packed(full, self.iterations, None)
-                    sl["out"].copy_(full.xyz)
-                self.compute_stream.synchronize()
-            return sl["out"].numpy().copy()
-        if int(sl["status"].max()) != 0:
-            # rare: some frames outgrew r_capacity -> exact synchronous re-run of the batch with the retrying path
-            ps = sl["ps"]
+        det, host, ps = sl.get("det"), sl["host"], sl["ps"]
+        if det is not None and int(det["setup_status_host"][0]) != 0:
+            # rare: the ROI patches outgrew the streaming buffer -> exact synchronous re-run of the batch through the
+            # exactly-sized, retrying path
+            from . import setup_gpu
             with torch.cuda.stream(self.compute_stream):
-                for k, dst in (("xyz", ps.xyz), ("scaling", ps.scaling), ("rotation", ps.rotation), ("opacity", ps.opacity)):
-                    dst.copy_(sl["host"][k], non_blocking=True)
-                optimize_packed(ps, self.iterations, None)
+                full = setup_gpu.pack_sequence_gpu(self.cfg, self.cams, host["poses_2d"], host.get("xyz"), self.device)
+                optimize_packed(full, self.iterations, None)
+                sl["out"].copy_(full.xyz)
+            self.compute_stream.synchronize()
+        elif int(sl["status"].max()) != 0:
+            # rare: some frames outgrew r_capacity -> exact re-run of THOSE frames from their initial state (the slot's ROI
+            # buffers are still intact: the slot is not reused before this call returns)
+            if self.r_capacity is not None:
+                raise _L.SkelSplatLibraryError(f"frame(s) exceeded r_capacity={self.r_capacity} (Gaussian,tile) pairs per view")
+            with torch.cuda.stream(self.compute_stream):
+                bad = torch.nonzero(sl["status"].to(self.device) != 0).flatten()
+                if det is None:
+                    init = tuple(host[k].to(self.device, non_blocking=True)[bad] for k in ("xyz", "scaling", "rotation", "opacity"))
+                else:
+                    if host.get("xyz") is not None:
+                        xyz0 = host["xyz"].to(self.device, non_blocking=True)[bad]
+                    else:
+                        from . import setup_gpu
+                        xyz0 = setup_gpu.triangulate_dlt(self._det["P"], det["p2d"][bad], self.device).to(torch.float32)
+                    init = (xyz0,) + tuple(t[bad] for t in self._det["tmpl"])
+                retry_overflowed(ps, bad, init, default_r_capacity(self.cfg), self.iterations)
                 sl["out"].copy_(ps.xyz)
             self.compute_stream.synchronize()
         return sl["out"].numpy().copy()

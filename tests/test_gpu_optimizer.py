@@ -157,11 +157,38 @@ def test_capacity_retry_is_transparent_and_exact():
     """Frames whose (Gaussian,tile) lists outgrow the default capacity are re-run from their initial state with a doubled
     capacity; the result equals a run that had the larger capacity from the start."""
     from dataclasses import replace
-    cfg = replace(configs.H36M, scaling=3.6)                       # larger splats: ~340 pairs per view > default 256
+    cfg = replace(configs.H36M, scaling=3.7)                       # larger splats: > 340 pairs per view > default 320
     seq = synthetic.make_sequence(cfg, 3, seed=17)
-    assert trainer.default_r_capacity(cfg) == 256
+    assert trainer.default_r_capacity(cfg) == 320
     with pytest.raises(Exception, match="r_capacity"):
         trainer.optimize_sequence(seq, DEV, iterations=40, r_capacity=256)
     auto = trainer.optimize_sequence(seq, DEV, iterations=40)       # default capacity + automatic retry
     big = trainer.optimize_sequence(seq, DEV, iterations=40, r_capacity=512)
     assert np.array_equal(auto, big)
+
+
+def test_streaming_retries_only_the_overflowed_frames():
+    """A streamed batch in which SOME frames outgrow the capacity: the status words flag them, result() re-runs just those
+    frames from their initial state (ROI buffers of the slot still intact) and returns what the resident path returns."""
+    from dataclasses import replace
+    cfg = replace(configs.H36M, scaling=3.7)
+    big = synthetic.make_sequence(cfg, 3, seed=17)
+    small = synthetic.make_sequence(configs.H36M, 3, seed=18)
+    pi = np.concatenate([np.stack([f.pose_3d_init for f in s.frames]) for s in (big, small)])
+    p2 = np.concatenate([np.stack([f.poses_2d for f in s.frames]) for s in (big, small)])
+    # frames 3..5 keep the default splat size: overwrite their raw scales after packing
+    h = trainer.pack_host(cfg, big.cameras, pi, p2)
+    h2 = trainer.pack_host(configs.H36M, big.cameras, pi[3:], p2[3:])
+    n_big = int(h["roi_offset"][3].min())
+    h["scaling"][3:] = h2["scaling"]; h["roi_rect"][3:] = h2["roi_rect"]; h["roi_offset"][3:] = h2["roi_offset"] + n_big
+    h["roi_data"] = np.concatenate([h["roi_data"][:n_big], h2["roi_data"]])
+    ps = trainer.pack_sequence(cfg, big.cameras, pi, p2, DEV, host=h)
+    st = trainer._launch(ps, trainer.make_opt_config(cfg, 320, 40), trainer.xyz_lr_table(cfg, ps.spatial_lr_scale, 40),
+                         torch.empty(6, device=DEV)).cpu().numpy()
+    assert st[:3].any() and not st[3:].any()                       # the premise: only the big-splat frames overflow
+    ps = trainer.pack_sequence(cfg, big.cameras, pi, p2, DEV, host=h)
+    ref = trainer.optimize_packed(ps, iterations=40)[0].cpu().numpy()
+    so = trainer.StreamingOptimizer(cfg, big.cameras, 6, int(h["roi_data"].size), DEV, iterations=40)
+    out = so.result(so.submit({k: torch.from_numpy(v).pin_memory() for k, v in h.items()}))
+    assert np.array_equal(out, ref)
+    assert so.launches == 1
