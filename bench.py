@@ -288,6 +288,16 @@ def run_ours(args):
                                   / traffic["optimize_kernel"]["frames_in_capture"]) if "optimize_kernel" in traffic else None),
                 "algorithmic_bytes_per_launch": round(bytes_launch),
                 "issue_slot_utilisation_ncu": (traffic["optimize_kernel"]["issue_active_pct"] / 100.0 if "optimize_kernel" in traffic else None),
+                # the roof that actually binds this kernel: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock).  Executed
+                # instructions per frame come from the committed ncu capture (data-dependent only through the synthetic seed); the
+                # duration is this run's.
+                "issue_roofline": ({"bound": "issue-slots", "unit": "G warp-inst/s",
+                                    "achieved": round(traffic["optimize_kernel"]["inst_executed"] * F / traffic["optimize_kernel"]["frames_in_capture"]
+                                                      / (kernel_ms / 1e3) / 1e9, 1),
+                                    "peak": round(148 * 4 * 1.965, 1), "peak_source": "148 SMs x 4 issue slots/clk x 1.965 GHz (clocks.max.sm)",
+                                    "frac": round(traffic["optimize_kernel"]["inst_executed"] * F / traffic["optimize_kernel"]["frames_in_capture"]
+                                                  / (kernel_ms / 1e3) / 1e9 / (148 * 4 * 1.965), 4)}
+                                   if "inst_executed" in traffic.get("optimize_kernel", {}) else None),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_view_iteration": round(bytes_view_iter, 1), "kernel_ms": round(kernel_ms, 3),
                 "note": "R2 is issue-slot/MUFU bound, not HBM bound (SURVEY.md 8d): see profiles/ for issue-slot utilisation; "
