@@ -10,18 +10,19 @@
 //   * parameters only change every `accumulation_steps` iterations, so the iterations of one step
 //     group are independent: they are processed concurrently as SLOTS "slots" (sequential depth 125
 //     instead of 500), each with its own binning state;
-//   * binning = (tile|depth) keys sorted by an in-shared-memory bitonic network (same keys and
-//     order as the dense rasteriser => same tile lists as the reference);
-//   * compositing is never materialised: each warp owns an active tile, walks its 8 row pairs,
-//     evaluates forward + loss + backward per pixel with the GT read from the ROI patch, keeps the
-//     per-(tile,Gaussian) gradient sums in registers and reduces them once per tile with a
-//     transposing shuffle butterfly (9 shuffles for 8 values) - no atomics, deterministic;
+//   * binning without a sort: every Gaussian's tiles form a rectangle and there are <= 20 Gaussians, so the
+//     position of a (Gaussian, tile) pair in the reference's (tile|depth)-sorted list has a closed form
+//     (phase B) => same tile lists, in the same order, as the reference's radix sort;
+//   * compositing is never materialised: each warp owns an active tile, walks the row pairs that can
+//     contribute, evaluates forward + loss + backward per pixel with the GT read from the ROI patch,
+//     keeps per-(tile,Gaussian) raw moment sums in registers and reduces them once per tile with a
+//     transposing shuffle butterfly (9 shuffles for 8 values) - no atomics, deterministic.  Tile lists of
+//     length 1 and 2 (84 % of the pairs) have hand-specialised functions (tile_one, tile_two);
 //   * the one-hot feature structure (Gaussian j renders only into channel j; frozen in the
 //     reference: scene/gaussian_model.py:159-166,186) collapses the reference's per-channel
 //     backward recurrence into one scalar recurrence per pixel;
 //   * Adam (torch.optim.Adam semantics, eps=1e-15) runs in-kernel with host-computed fp64 step sizes.
 #include <cmath>
-#include <vector>
 #include "common.cuh"
 #include "api_internal.h"
 
@@ -34,11 +35,8 @@ constexpr int OPT_THREADS = SSB_OPT_THREADS;
 #ifndef SSB_OPT_MIN_CTAS
 #define SSB_OPT_MIN_CTAS 2
 #endif
-#ifndef SSB_PP_N1           // pixels per lane and trip for tile lists of length 1 / 2 (see tile_fast)
-#define SSB_PP_N1 2
-#endif
-#ifndef SSB_PP_N2
-#define SSB_PP_N2 1
+#ifndef SSB_PP_N1           // pixels per lane and loop trip in tile_one (2: two independent dependency chains per lane;
+#define SSB_PP_N1 2          // the same for tile lists of length 2 measured slower)
 #endif
 #ifndef SSB_ROWCULL          // exact row-band culling as warp-uniform pass-loop bounds (0: all 8 passes; bitwise-identical results).
 #define SSB_ROWCULL 1        // An earlier per-(pass, entry) predicate form of the same test measured 8 % SLOWER and was dropped.
