@@ -38,6 +38,9 @@ constexpr int OPT_THREADS = SSB_OPT_THREADS;
 #ifndef SSB_PP_N1           // pixels per lane and loop trip in tile_one (2: two independent dependency chains per lane;
 #define SSB_PP_N1 2          // the same for tile lists of length 2 measured slower)
 #endif
+#ifndef SSB_FAST_MAX         // longest tile list with a fully unrolled register-resident tile function (longer: chunked generic path)
+#define SSB_FAST_MAX 4
+#endif
 #ifndef SSB_ROWCULL          // exact row-band culling as warp-uniform pass-loop bounds (0: all 8 passes; bitwise-identical results).
 #define SSB_ROWCULL 1        // An earlier per-(pass, entry) predicate form of the same test measured 8 % SLOWER and was dropped.
 #endif
@@ -653,8 +656,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 #define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
                 if (n == 1) { const int g1 = list[0]; tile_one<SSB_PP_N1>(sp, g1, s_roi[v][g1], s_roi_rel[v][g1], roi_base, lx, ly0, W, H, part_out, lane); }
                 else if (n == 2) tile_two(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
-                else if (n == 3) SSB_TILE_FAST(3, 1)
-                else if (n == 4) SSB_TILE_FAST(4, 1)
+                else if (n == 3 && SSB_FAST_MAX >= 3) SSB_TILE_FAST(3, 1)
+                else if (n == 4 && SSB_FAST_MAX >= 4) SSB_TILE_FAST(4, 1)
 #undef SSB_TILE_FAST
                 else {
                     // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
