@@ -29,5 +29,10 @@ trainer.optimize_packed(ps)
 torch.cuda.synchronize()
 lib.ssb_debug_phase_cycles(out, 0)
 tot = float(sum(out))
+hist = (C.c_ulonglong * 24)()
+lib.ssb_debug_list_hist(hist)
+ht = float(sum(hist)); he = float(sum(i * hist[i] for i in range(24)))
+print(json.dumps({"tiles_by_list_length": {i: round(hist[i] / ht, 4) for i in range(24) if hist[i]},
+                  "pairs_by_list_length": {i: round(i * hist[i] / he, 4) for i in range(24) if hist[i]}}))
 print(json.dumps({"config": name, "frames": F, "share": {n: round(out[i] / tot, 4) for i, n in enumerate(NAMES)},
                   "cycles_per_frame_step": {n: round(out[i] / F / (cfg.iterations // cfg.accumulation_steps)) for i, n in enumerate(NAMES)}}))

@@ -23,6 +23,7 @@
 //     backward recurrence into one scalar recurrence per pixel;
 //   * Adam (torch.optim.Adam semantics, eps=1e-15) runs in-kernel with host-computed fp64 step sizes.
 #include <cmath>
+#include <type_traits>
 #include "common.cuh"
 #include "api_internal.h"
 
@@ -38,8 +39,8 @@ constexpr int OPT_THREADS = SSB_OPT_THREADS;
 #ifndef SSB_PP_N1           // pixels per lane and loop trip in tile_one (2: two independent dependency chains per lane;
 #define SSB_PP_N1 2          // the same for tile lists of length 2 measured slower)
 #endif
-#ifndef SSB_FAST_MAX         // longest tile list with a fully unrolled register-resident tile function (longer: chunked generic path)
-#define SSB_FAST_MAX 4
+#ifndef SSB_FAST_MAX         // longest tile list with a fully unrolled register-resident tile function compiled in (longer lists:
+#define SSB_FAST_MAX 5       // chunked generic path).  ssb_opt_config::max_unrolled_list selects 4 or 5 at run time (tuning knob).
 #endif
 #ifndef SSB_ROWCULL          // exact row-band culling as warp-uniform pass-loop bounds (0: all 8 passes; bitwise-identical results).
 #define SSB_ROWCULL 1        // An earlier per-(pass, entry) predicate form of the same test measured 8 % SLOWER and was dropped.
@@ -49,6 +50,7 @@ constexpr int OPT_THREADS = SSB_OPT_THREADS;
 #endif
 #if SSB_PHASE_TIMING
 __device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_list_hist[24];      // tiles by list length (index min(n, 23))
 #define SSB_PHASE_MARK(i) { if (tid == 0) { const long long t_now = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_now - t_phase)); t_phase = t_now; } }
 #else
 #define SSB_PHASE_MARK(i)
@@ -154,11 +156,14 @@ __device__ __forceinline__ bool pair_alpha_hoisted(float gpy, float conz, float 
     return !(alpha < ALPHA_MIN);
 }
 
-// Loss-mask count, loss term and raw moment sums of one contributing (pixel, Gaussian) pair.
-__device__ __forceinline__ void pair_accumulate(float (&acc)[PSTRIDE], float dx, float dy, float G, float Tb, float err, float S, float gt) {
+// Loss-mask count, loss term and raw moment sums of one contributing (pixel, Gaussian) pair.  The loss term and the count
+// are only ever used as totals over all Gaussians of a view (phase D), so a tile with several Gaussians keeps ONE pair of
+// them (in the record of its first entry) and 6 moment sums per entry: 6N + 2 instead of 8N live registers.
+__device__ __forceinline__ void pair_accumulate(float (&acc)[PSTRIDE], float& loss, float& count, float dx, float dy, float G, float Tb,
+                                                float err, float S, float gt) {
     const float gpos = fmaxf(gt, 0.f);
-    acc[7] += (gt > 0.f) ? 0.f : 1.f;                              // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
-    acc[6] = fmaf(-gpos, gpos, fmaf(err, err, acc[6]));            // err^2 - [gt > 0] gt^2
+    count += (gt > 0.f) ? 0.f : 1.f;                               // mask pixel outside {gt > 0} (exact in fp32: < 2^24)
+    loss = fmaf(-gpos, gpos, fmaf(err, err, loss));                // err^2 - [gt > 0] gt^2
     pair_backward(acc, dx, dy, G, Tb, err, S);
 }
 
@@ -188,7 +193,8 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
     // contain no contributing pixel at all.
     int gid[N], gw2[N];
     const float* gptr[N];                                          // the lane's column in row ly0 of patch u (may lie outside it)
-    unsigned gmask = 0u;                                           // bit (8u + pass): the lane's pixel of that pass lies in patch u
+    typedef typename std::conditional<(N > 4), unsigned long long, unsigned>::type mask_t;
+    mask_t gmask = 0;                                              // bit (8u + pass): the lane's pixel of that pass lies in patch u
     const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
     int vlo = TILE / 2, vhi = -1;
 #pragma unroll
@@ -204,12 +210,12 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
         int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                 // first pass with ry0 + 2*pass >= 0
         int phi = (roi.w - ry0 + 1) >> 1;                          // first pass with ry0 + 2*pass >= h
         phi = phi > TILE / 2 ? TILE / 2 : phi;
-        if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
+        if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (mask_t)(((1u << (phi - plo)) - 1u) << plo) << (8 * u);
         gptr[u] = roi_base + (roi_rel_v[g] + ry0 * roi.z + rx);
         asm volatile("" : "+l"(gptr[u]));   // keep the finished 64-bit pointer (else base + offset is re-derived per load)
         gw2[u] = 2 * roi.z;
     }
-    float accv[N][PSTRIDE];
+    float accv[N][PSTRIDE];           // [u][6], [u][7] (loss term, count) are used for u == 0 only: see pair_accumulate
 #pragma unroll
     for (int u = 0; u < N; u++)
 #pragma unroll
@@ -223,13 +229,13 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
             // GT values of the listed Gaussians' channels at the lane's pixels: issued first, consumed only in the backward
             // replay, so the L2 latency hides behind the forward math (a pixel outside a patch reads nothing and gets 0)
             float gtv[PP][N];
-            const unsigned gm = gmask >> pass0;
+            const mask_t gm = gmask >> pass0;
 #pragma unroll
             for (int q = 0; q < PP; q++) {
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if (gm & (1u << (8 * u + q))) gtv[q][u] = __ldg(gptr[u] + (pass0 + q) * gw2[u]);
+                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = __ldg(gptr[u] + (pass0 + q) * gw2[u]);
                 }
             }
             float pyf[PP];
@@ -284,7 +290,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
                             const float err = fmaf(al[q][u], Tb[q][u], -gt);    // rendered value of channel g minus GT
                             S[q] = fmaf(last_alpha[q], last_g[q] - S[q], S[q]);  // S <- a_last g_last + (1 - a_last) S
                             last_g[q] = err; last_alpha[q] = al[q][u];
-                            pair_accumulate(accv[u], dx, dy, Gv[q][u], Tb[q][u], err, S[q], gt);
+                            pair_accumulate(accv[u], accv[0][6], accv[0][7], dx, dy, Gv[q][u], Tb[q][u], err, S[q], gt);
                         }
                     }
                 }
@@ -340,7 +346,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
                         const float G = expf(power);
                         const float alpha = fminf(ALPHA_MAX, __fmul_rn(A.z, G));
                         if (!(alpha < ALPHA_MIN)) {
-                            pair_accumulate(acc, dx, dy, G, 1.0f, alpha - gtv[q], 0.0f, gtv[q]);   // err = rendered - GT
+                            pair_accumulate(acc, acc[6], acc[7], dx, dy, G, 1.0f, alpha - gtv[q], 0.0f, gtv[q]);   // err = rendered - GT
                         }
                     }
                 }
@@ -405,10 +411,10 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
                 float S = 0.f;
                 if (v1) {
                     const float err1 = fmaf(a1, T1, -gt1);
-                    pair_accumulate(acc1, dx1, dy1, G1, T1, err1, 0.f, gt1);
+                    pair_accumulate(acc1, acc0[6], acc0[7], dx1, dy1, G1, T1, err1, 0.f, gt1);
                     S = a1 * err1;
                 }
-                if (v0) pair_accumulate(acc0, dx0, dy0, G0, 1.0f, a0 - gt0, S, gt0);
+                if (v0) pair_accumulate(acc0, acc0[6], acc0[7], dx0, dy0, G0, 1.0f, a0 - gt0, S, gt0);
             }
         }
     }
@@ -633,6 +639,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         // every result is a per-(tile,Gaussian) record, so the schedule does not influence any sum ============
         {
             const float* roi_base = p.roi_data + s_roi_base;
+            const bool unroll5 = p.cfg.max_unrolled_list != 4;          // 0 (default) or 5: lists of five take tile_fast<5>
             // one counter per slot; a warp starts on slot (warp mod SLOTS) and moves on when that slot's tiles are handed out,
             // so everything that depends on the slot only (view, image size, splat table) is loaded once per slot, not per tile
             for (int kk = 0; kk < SLOTS; kk++) {
@@ -651,6 +658,9 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 const int e1 = (a + 1 < nact) ? (int)d_start[(size_t)k * RCAP + a + 1] : s_R[k];
                 const int n = e1 - e0;
                 const uint16_t* list = d_list + (size_t)k * RCAP + e0;
+#if SSB_PHASE_TIMING
+                if (lane == 0) atomicAdd(&g_list_hist[n < 23 ? n : 23], 1ull);
+#endif
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
 #define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
@@ -658,6 +668,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 else if (n == 2) tile_two(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
                 else if (n == 3 && SSB_FAST_MAX >= 3) SSB_TILE_FAST(3, 1)
                 else if (n == 4 && SSB_FAST_MAX >= 4) SSB_TILE_FAST(4, 1)
+                else if (n == 5 && SSB_FAST_MAX >= 5 && unroll5) SSB_TILE_FAST(5, 1)
+                else if (n == 6 && SSB_FAST_MAX >= 6) SSB_TILE_FAST(6, 1)
 #undef SSB_TILE_FAST
                 else {
                     // ---------- generic path (long tile lists): entries in chunks of FAST, replayed per chunk
@@ -871,6 +883,9 @@ int ssb_debug_phase_cycles(unsigned long long* out8, int reset) {
     if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
     return SSB_OK;
 }
+int ssb_debug_list_hist(unsigned long long* out24) {
+    return cudaMemcpyFromSymbol(out24, g_list_hist, sizeof(unsigned long long) * 24) == cudaSuccess ? SSB_OK : SSB_ERR_CUDA;
+}
 #endif
 
 size_t ssb_optimize_workspace_bytes(const ssb_opt_config* cfg, int n_frames) {
@@ -887,6 +902,7 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
     if (cfg->J <= 0 || cfg->J > MAXJ || cfg->V <= 0 || cfg->V > MAXV || cams->n_views != cfg->V) return SSB_ERR_UNSUPPORTED;
     if (cfg->accumulation_steps < 1 || cfg->accumulation_steps > MAX_SLOTS || cfg->accumulation_steps == 3) return SSB_ERR_UNSUPPORTED;
     if (cfg->r_capacity < 32 || cfg->r_capacity > 1024 || (cfg->r_capacity % 32)) return SSB_ERR_CAPACITY;
+    if (cfg->max_unrolled_list != 0 && cfg->max_unrolled_list != 4 && cfg->max_unrolled_list != 5) return SSB_ERR_INVALID;
     const int n_steps = cfg->iterations / cfg->accumulation_steps;   // trailing iterations never reach an optimiser step
     if (n_steps > MAX_STEPS) return SSB_ERR_CAPACITY;
     for (int i = 0; i < 8; i++) if (cfg->limb_pairs[i] < 0 || cfg->limb_pairs[i] >= cfg->J) return SSB_ERR_INVALID;

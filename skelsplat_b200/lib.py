@@ -39,7 +39,7 @@ class OptConfig(C.Structure):
                 ("lambda_consistency", C.c_float), ("limb_pairs", C.c_int * 8),
                 ("lr_scaling", C.c_float), ("lr_rotation", C.c_float), ("lr_opacity", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("r_capacity", C.c_int), ("antialiasing", C.c_int)]
+                ("r_capacity", C.c_int), ("antialiasing", C.c_int), ("max_unrolled_list", C.c_int)]
 
 
 _lib = None
