@@ -181,7 +181,7 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
     __shared__ float s_col[256];
     __shared__ double s_row[256];
     __shared__ float s_max;
-    if (w > 256 || h > 256) {                  // sigma > 31 px: not a SkelSplat regime
+    if (w > 256 || h > 256 || rx > 128 || ry > 128) {      // sigma > 31 px: not a SkelSplat regime
         if (status && threadIdx.x == 0) atomicOr(status, (int)SSB_STATUS_ROI_TOO_WIDE);
         return;
     }
@@ -189,9 +189,21 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
         if (status && threadIdx.x == 0) atomicOr(status, (int)SSB_STATUS_ROI_OVERFLOW);
         return;
     }
-    double wy = 0.0, wx = 0.0;
-    for (int k = -ry; k <= ry; k++) wy += exp(-0.5 / (s1 * s1) * (double)(k * k));
-    for (int k = -rx; k <= rx; k++) wx += exp(-0.5 / (s2 * s2) * (double)(k * k));
+    // normalisation sums of the two truncated kernels: one term per thread, then summed by ONE thread in the sequential
+    // order k = -r..r (the order scipy's / the host generator's loop uses), so the value does not depend on the block shape
+    __shared__ double s_term[2][2 * 128 + 1];
+    __shared__ double s_wsum[2];
+    for (int k = threadIdx.x; k <= 2 * ry; k += blockDim.x) s_term[0][k] = exp(-0.5 / (s1 * s1) * (double)((k - ry) * (k - ry)));
+    for (int k = threadIdx.x; k <= 2 * rx; k += blockDim.x) s_term[1][k] = exp(-0.5 / (s2 * s2) * (double)((k - rx) * (k - rx)));
+    __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const int a = threadIdx.x ? 1 : 0, r = a ? rx : ry;
+        double acc = 0.0;
+        for (int k = 0; k <= 2 * r; k++) acc += s_term[a][k];
+        s_wsum[a] = acc;
+    }
+    __syncthreads();
+    const double wy = s_wsum[0], wx = s_wsum[1];
     for (int t = threadIdx.x; t < h; t += blockDim.x) s_col[t] = (float)(255.0 * reflect_response(y0 + t, yc, H, s1, ry, 1.0 / wy));
     for (int t = threadIdx.x; t < w; t += blockDim.x) s_row[t] = reflect_response(x0 + t, xc, W, s2, rx, 1.0 / wx);
     __syncthreads();
@@ -210,33 +222,42 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
     }
 }
 
-// Exclusive scan of the patch sizes into packed offsets (+ the total), one CTA: n = F*V*J is ~1e5, a few microseconds.
-// Keeps the detections -> ROIs -> optimiser pipeline free of host round trips.
+// Exclusive scan of the patch sizes into packed offsets (+ the total), one CTA of 32 warps: warp w owns the contiguous
+// segment [w*seg, (w+1)*seg) and walks it 32 elements at a time (coalesced), first to get the segment sums, then -- after a
+// scan of the 32 segment sums -- to write the offsets.  n = F*V*J is ~1e5: ~10 us, and it keeps the
+// detections -> ROIs -> optimiser pipeline free of host round trips.
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS)
 roi_offsets_kernel(long long n, const long long* __restrict__ size, long long* __restrict__ offset, long long* __restrict__ total)
 {
-    __shared__ long long s_warp[SCAN_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-    const long long b = per * tid, e = (b + per < n) ? b + per : n;
+    __shared__ long long s_seg[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long seg = ((n + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32) + 31) / 32 * 32;      // multiple of 32 elements
+    const long long b = seg * warp, e = (b + seg < n) ? b + seg : n;
     long long sum = 0;
-    for (long long i = b; i < e; i++) sum += size[i];
-    long long incl = sum;                                          // inclusive scan of the per-thread sums
+    for (long long i = b + lane; i < e; i += 32) sum += size[i];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) s_warp[warp] = incl;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) s_seg[warp] = sum;
     __syncthreads();
-    if (warp == 0) {
-        long long w = s_warp[lane];
+    if (warp == 0) {                                               // inclusive scan of the segment sums
+        long long w = s_seg[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= o) w += t; }
-        s_warp[lane] = w;
+        s_seg[lane] = w;
     }
     __syncthreads();
-    long long run = incl - sum + (warp ? s_warp[warp - 1] : 0);
-    for (long long i = b; i < e; i++) { offset[i] = run; run += size[i]; }
-    if (tid == SCAN_THREADS - 1 && total) *total = s_warp[SCAN_THREADS / 32 - 1];
+    long long run = warp ? s_seg[warp - 1] : 0;                    // elements before this segment
+    for (long long i0 = b; i0 < e; i0 += 32) {
+        const long long i = i0 + lane;
+        const long long v = (i < e) ? size[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        if (i < e) offset[i] = run + incl - v;
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (threadIdx.x == 0 && total) *total = s_seg[SCAN_THREADS / 32 - 1];
 }
 
 }  // namespace ssb
