@@ -31,7 +31,8 @@ extern "C" {
 #define SSB_STATUS_ROI_OVERFLOW 2u /* heatmap patches need more than the roi_data capacity given: patches were skipped */
 #define SSB_STATUS_ROI_TOO_WIDE 4u /* a heatmap patch is wider than 256 px (sigma > 31 px): outside the supported regime */
 
-int         ssb_version(void);
+int         ssb_version(void);              /* 101: ssb_opt_config grew max_unrolled_list; roi_fill takes a capacity */
+int         ssb_struct_size(int which);     /* sizeof: 0 ssb_gaussians, 1 ssb_cameras, 2 ssb_opt_config; -1 otherwise */
 const char* ssb_error_string(int code);
 const char* ssb_last_cuda_error(void);
 /* Channel counts the templated kernels are instantiated for (reference: NUM_CHANNELS in

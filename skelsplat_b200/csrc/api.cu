@@ -11,7 +11,16 @@ int ssb_set_cuda_error(cudaError_t e) {
 }
 
 extern "C" {
-int ssb_version(void) { return 100; }
+int ssb_version(void) { return 101; }
+// sizeof of the ABI structs (0: ssb_gaussians, 1: ssb_cameras, 2: ssb_opt_config): lets a binding verify its struct layout
+int ssb_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(ssb_gaussians);
+        case 1: return (int)sizeof(ssb_cameras);
+        case 2: return (int)sizeof(ssb_opt_config);
+        default: return -1;
+    }
+}
 const char* ssb_last_cuda_error(void) { return g_last_cuda_error; }
 const char* ssb_error_string(int code) {
     switch (code) {

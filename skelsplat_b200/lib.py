@@ -45,7 +45,7 @@ class OptConfig(C.Structure):
 _lib = None
 
 EXPORTS = [
-    "ssb_version", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
+    "ssb_version", "ssb_struct_size", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
     "ssb_state_bytes", "ssb_rasterize_forward", "ssb_backward_scratch_bytes", "ssb_rasterize_backward",
     "ssb_mark_visible", "ssb_state_field_offset",
     "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency",
@@ -77,6 +77,10 @@ def lib():
         L.ssb_backward_scratch_bytes.restype = C.c_size_t
         L.ssb_state_field_offset.restype = C.c_int64
         L.ssb_optimize_workspace_bytes.restype = C.c_size_t
+        for which, struct in enumerate((Gaussians, Cameras, OptConfig)):      # the ctypes mirrors must match the header
+            if L.ssb_struct_size(C.c_int(which)) != C.sizeof(struct):
+                raise SkelSplatLibraryError(f"{LIB_PATH}: struct layout mismatch for {struct.__name__} "
+                                            f"({L.ssb_struct_size(C.c_int(which))} vs {C.sizeof(struct)} bytes): rebuild the library")
         _lib = L
     return _lib
 

@@ -50,6 +50,21 @@ def test_version_and_error_strings():
         assert L.ssb_channels_supported(C.c_int(c)) == ok
 
 
+def test_ctypes_structs_match_the_header_layout():
+    """The library reports sizeof() of its ABI structs; the ctypes mirrors (what INTEGRATION.md tells a binding to write)
+    must agree, and a config with an unknown tuning value is rejected."""
+    from skelsplat_b200 import lib
+    L = lib.lib()
+    for which, struct in enumerate((lib.Gaussians, lib.Cameras, lib.OptConfig)):
+        assert L.ssb_struct_size(C.c_int(which)) == C.sizeof(struct)
+    assert L.ssb_struct_size(C.c_int(7)) == -1
+    oc = lib.OptConfig()
+    oc.J, oc.V, oc.iterations, oc.accumulation_steps, oc.r_capacity, oc.max_unrolled_list = 17, 4, 500, 4, 320, 3
+    lr = (C.c_double * 501)()
+    assert L.ssb_optimize_frames(C.byref(oc), C.c_int(1), C.byref(lib.Cameras(4, None, None, None, None, 100, 100, 0.5, 0.5, 0)), lr,
+                                 None, None, None, None, None, None, None, None, None, None) == -1
+
+
 def test_state_layout_is_monotonic_and_aligned():
     from skelsplat_b200 import lib
     P, W, H, rc = 17, 1002, 1000, 2048
