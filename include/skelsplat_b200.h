@@ -178,7 +178,7 @@ typedef struct ssb_opt_config {
     float beta1, beta2, eps;    /* 0.9, 0.999, 1e-15 */
     int   r_capacity;           /* max (Gaussian,tile) pairs per view: a multiple of 32, 32..1024 */
     int   antialiasing;
-    int   max_unrolled_list;    /* tuning knob, results do not depend on it: tile lists of 5 Gaussians take the unrolled
+    int   max_unrolled_list;    /* tuning knob (same arithmetic, different fp32 summation order): tile lists of 5 Gaussians take the unrolled
                                    register-resident path (0 = default = 5) or the chunked generic path (4) */
 } ssb_opt_config;
 
