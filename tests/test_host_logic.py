@@ -153,3 +153,31 @@ def test_fused_path_rejects_losses_the_reference_loop_cannot_run():
     with pytest.raises(NotImplementedError):
         trainer.make_opt_config(bad)
     assert trainer.make_opt_config(configs.H36M).J == 17
+
+
+@pytest.mark.parametrize("name,seed", [("h36m", 0), ("panoptic", 1), ("occlusion-person", 2), ("h36m", 3)])
+def test_closed_form_sorted_positions_equal_the_reference_sort(name, seed):
+    """The fused optimiser bins without sorting: the closed-form position of every (Gaussian, tile) pair must reproduce the
+    order of the reference's stable (tile | depth) radix sort -- checked here against the C oracle's sort on random,
+    overlapping, partly culled Gaussians (equal depths included)."""
+    from oracle import rast
+    from skelsplat_b200 import binning
+    from tests.util import raster_case
+    cfg = small_config(configs.get_config(name), 2)
+    case = raster_case(cfg, seed=seed, n_views=1, big=(seed != 3))
+    means = case["means3D"].copy()
+    means[2] = means[0]                                         # identical centres: equal depth bits, order decided by id
+    means[3, 2] -= 5000.0                                       # behind the camera: culled, touches no tile
+    W, H = int(case["dims"][0, 0]), int(case["dims"][0, 1])
+    fw = rast.forward(means, case["scales"], case["rotations"], case["opacities"], case["features"], case["viewmatrix"][0],
+                      case["projmatrix"][0], W, H, float(case["tanfov"][0, 0]), float(case["tanfov"][0, 1]))
+    rects = fw["rects"].astype(np.int64).copy()                 # (x0, y0, x1, y1) per Gaussian
+    rects[fw["radii"] <= 0] = 0
+    gs, xy, pos = binning.sorted_positions(rects, fw["depths"].view(np.uint32))
+    R = fw["R"]
+    assert len(pos) == R and sorted(pos.tolist()) == list(range(R))       # a permutation of 0..R-1
+    gx = (W + 15) // 16
+    assert np.array_equal(gs[np.argsort(pos)], fw["point_list"].astype(np.int64))
+    tiles_sorted = (fw["keys_sorted"] >> np.uint64(32)).astype(np.int64)
+    assert np.array_equal((xy[:, 1] * gx + xy[:, 0])[np.argsort(pos)], tiles_sorted)
+    assert (fw["radii"] <= 0).any() and R > 40
