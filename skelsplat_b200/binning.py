@@ -39,3 +39,19 @@ def sorted_positions(rects, depth_bits):
                             p += 1                                                  # same tile, nearer Gaussian
                 gs.append(j); xy.append((x, y)); pos.append(p)
     return np.asarray(gs, np.int64), np.asarray(xy, np.int64).reshape(-1, 2), np.asarray(pos, np.int64)
+
+
+def row_band(py, conx, cony, conz):
+    """Pixel rows [rlo, rhi] outside which a splat cannot reach alpha >= 1/255 (optimizer.cu, phase A): for a fixed dy the largest
+    power over dx is -0.5 dy^2 det/conx, which must be >= -5.55 (pair_alpha's early-out threshold; opacity <= 1), so
+    |dy| <= sqrt(11.1 conx/det), widened by 1 % + 1 px against fp32 rounding; a near-singular conic gets no band."""
+    f = np.float32
+    py, conx, cony, conz = f(py), f(conx), f(cony), f(conz)
+    cdet = f(f(conx * conz) - f(cony * cony))
+    if conx > 0 and cdet > f(1e-4) * conx * conz:
+        ey = f(1.01) * np.sqrt(f(11.1) * conx / cdet, dtype=np.float32) + f(1.0)
+    else:
+        ey = f(1e9)
+    rlo = int(min(max(np.ceil(py - ey), 0.0), 65535.0))
+    rhi = int(min(max(np.floor(py + ey), -1.0), 65535.0))
+    return rlo, rhi

@@ -181,3 +181,34 @@ def test_closed_form_sorted_positions_equal_the_reference_sort(name, seed):
     tiles_sorted = (fw["keys_sorted"] >> np.uint64(32)).astype(np.int64)
     assert np.array_equal((xy[:, 1] * gx + xy[:, 0])[np.argsort(pos)], tiles_sorted)
     assert (fw["radii"] <= 0).any() and R > 40
+
+
+def test_row_band_contains_every_contributing_pixel():
+    """Exactness of the row culling: brute force over pixels with the reference's fp32 power expression (forward.cu:352-364)
+    never finds a contributing pixel (power >= -5.55, the cut used with opacity <= 1) outside the band, for isotropic, elongated,
+    rotated, tiny and huge splats."""
+    from skelsplat_b200 import binning
+    rng = np.random.default_rng(0)
+    f = np.float32
+    checked = 0
+    for trial in range(300):
+        s1, s2 = np.exp(rng.uniform(-0.5, 4.0, 2))                       # std devs 0.6 .. 55 px
+        th = rng.uniform(0, np.pi)
+        Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        cov = Rm @ np.diag([s1 * s1, s2 * s2]) @ Rm.T + 0.3 * np.eye(2)
+        inv = np.linalg.inv(cov)
+        conx, cony, conz = f(inv[0, 0]), f(inv[0, 1]), f(inv[1, 1])
+        px, py = f(rng.uniform(100, 400)), f(rng.uniform(100, 400))
+        rlo, rhi = binning.row_band(py, conx, cony, conz)
+        ys, xs = np.mgrid[0:512, 0:512]
+        dx = (px - xs.astype(f)).astype(f); dy = (py - ys.astype(f)).astype(f)
+        t = (dy * (dy * conz).astype(f)).astype(f)
+        t = (dx * (dx * conx).astype(f) + t).astype(f)
+        power = (t * f(-0.5) - (dy * (dx * cony).astype(f)).astype(f)).astype(f)
+        rows = np.nonzero(((power <= 0) & (power >= f(-5.55))).any(axis=1))[0]
+        if rows.size:
+            assert rlo <= rows.min() and rows.max() <= rhi, (trial, rlo, rhi, rows.min(), rows.max())
+            checked += 1
+            if 8 < rows.min() and rows.max() < 500:                       # and the band is tight: a few rows of slack at most
+                assert rows.min() - rlo <= 3 + 0.011 * (rows.max() - rows.min()) and rhi - rows.max() <= 3 + 0.011 * (rows.max() - rows.min())
+    assert checked > 250
