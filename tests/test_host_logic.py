@@ -212,3 +212,41 @@ def test_row_band_contains_every_contributing_pixel():
             if 8 < rows.min() and rows.max() < 500:                       # and the band is tight: a few rows of slack at most
                 assert rows.min() - rlo <= 3 + 0.011 * (rows.max() - rows.min()) and rhi - rows.max() <= 3 + 0.011 * (rows.max() - rows.min())
     assert checked > 250
+
+
+def test_fused_one_hot_backward_equals_the_reference_backward():
+    """The algebra of the fused kernel (one scalar recurrence per pixel, raw moment sums, mask size from per-pair counts,
+    constants applied once) against the C oracle of the reference's forward + per-channel backward fed with the l2_gaussian
+    gradient: same image, loss, N and per-Gaussian gradients."""
+    from oracle import rast
+    from skelsplat_b200 import fused_math
+    from tests.util import raster_case, relerr
+    cfg = small_config(configs.H36M, 8)
+    case = raster_case(cfg, seed=5, n_views=1, big=True)
+    J = case["means3D"].shape[0]
+    feats = np.eye(J, dtype=np.float32)
+    W, H = int(case["dims"][0, 0]), int(case["dims"][0, 1])
+    args = (case["viewmatrix"][0], case["projmatrix"][0], W, H, float(case["tanfov"][0, 0]), float(case["tanfov"][0, 1]))
+    fw = rast.forward(case["means3D"], case["scales"], case["rotations"], case["opacities"], feats, *args)
+    rng = np.random.default_rng(1)
+    ys, xs = np.mgrid[0:H, 0:W]
+    gt = np.zeros((J, H, W), np.float32)
+    for j in range(J):                                          # GT blobs near (not at) the splats, exactly zero elsewhere
+        cx, cy = fw["means2D"][j] + rng.normal(0, 6, 2)
+        blob = np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * 7.0 ** 2))
+        gt[j] = np.where(blob > 0.05, blob, 0).astype(np.float32)
+    out = fused_math.view_iteration(fw["means2D"], fw["conic_opacity"], fw["ranges"], fw["point_list"], gt, W, H)
+    assert relerr(out["render"], fw["color"]) < 1e-6
+    render = fw["color"]
+    mask = (gt > 0) | (render > 0)
+    N = int(mask.sum())
+    assert out["N"] == N and 0 < (render > 0).sum() < render.size
+    loss = float((((render - gt).astype(np.float64)) ** 2)[mask].sum() / N)
+    assert abs(out["loss"] - loss) < 1e-6 * loss
+    dL = np.where(mask, 2.0 * (render - gt) / N, 0).astype(np.float32)
+    bw = rast.backward(fw, case["means3D"], case["scales"], case["rotations"], feats, *args, dL)
+    assert relerr(out["dL_dmean2D"], bw["dL_dmeans2D"][:, :2]) < 1e-4
+    ref_conic = np.stack([bw["dL_dconic"][:, 0, 0], bw["dL_dconic"][:, 0, 1], bw["dL_dconic"][:, 1, 1]], 1)
+    assert relerr(out["dL_dconic"], ref_conic) < 1e-4
+    assert relerr(out["dL_dopacity"], bw["dL_dopacity"][:, 0]) < 1e-4
+    assert np.abs(bw["dL_dmeans2D"]).max() > 0
