@@ -63,3 +63,21 @@ def view_iteration(means2D, conic_opacity, ranges, point_list, gt, W, H):
     return dict(dL_dmean2D=np.stack([-(cx * t + cy * u) * 0.5 * W, -(cz * u + cy * t) * 0.5 * H], 1) / N,
                 dL_dconic=np.stack([-op * r[:, 2], -op * r[:, 3], -op * r[:, 4]], 1) / N, dL_dopacity=2 * r[:, 5] / N,
                 loss=loss, N=N, render=render)
+
+
+def adam_step_fp32(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-15):
+    """One torch.optim.Adam step exactly as the fused kernel performs it (optimizer.cu phase E + the host step table):
+    python-float (fp64) host scalars step_size = lr / (1 - beta1^t) and sqrt(1 - beta2^t), rounded to fp32 where torch hands
+    them to an fp32 tensor op; then lerp / mul+addcmul / sqrt / div / add / addcdiv in fp32.  Arrays are float32, updated
+    copies are returned.  tests/test_host_logic.py checks bit-equality with torch.optim.Adam (foreach path)."""
+    f = np.float32
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    neg_step = f(-(lr / bc1))
+    bc2_sqrt = f(np.sqrt(bc2))
+    m = (m + f(1.0 - beta1) * (grad - m)).astype(f)                                  # lerp_(grad, 1 - beta1)  (fma in the kernel)
+    v = (f(beta2) * v).astype(f)
+    v = (v + (f(1.0 - beta2) * grad).astype(f) * grad).astype(f)                      # addcmul_(grad, grad, value=1 - beta2)
+    denom = ((np.sqrt(v).astype(f) / bc2_sqrt).astype(f) + f(eps)).astype(f)
+    param = (param + neg_step * (m / denom).astype(f)).astype(f)                      # addcdiv_(m, denom, value=-step_size)
+    return param, m, v

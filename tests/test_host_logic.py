@@ -250,3 +250,27 @@ def test_fused_one_hot_backward_equals_the_reference_backward():
     assert relerr(out["dL_dconic"], ref_conic) < 1e-4
     assert relerr(out["dL_dopacity"], bw["dL_dopacity"][:, 0]) < 1e-4
     assert np.abs(bw["dL_dmeans2D"]).max() > 0
+
+
+def test_adam_mirror_matches_torch_adam():
+    """The in-kernel Adam (host fp64 step sizes rounded to fp32, eps = 1e-15 added AFTER the bias-corrected sqrt) against
+    torch.optim.Adam on the CPU, including the noise-level gradients that eps = 1e-15 turns into full-size steps."""
+    from skelsplat_b200 import fused_math
+    rng = np.random.default_rng(0)
+    n = 64
+    p0 = rng.normal(0, 100, n).astype(np.float32)
+    grads = [(rng.normal(0, 1, n) * 10.0 ** rng.uniform(-12, 1, n)).astype(np.float32) for _ in range(6)]
+    lrs = [2.5 * 0.97 ** s for s in range(6)]                   # the xyz group's lr changes every step (update_learning_rate)
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([{"params": [tp], "lr": 0.0}], lr=0.0, eps=1e-15)
+    p, m, v = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for s, (g, lr) in enumerate(zip(grads, lrs), start=1):
+        opt.param_groups[0]["lr"] = lr
+        tp.grad = torch.from_numpy(g.copy())
+        opt.step()
+        before = p.copy()
+        p, m, v = fused_math.adam_step_fp32(p, g, m, v, s, lr)
+        step_ours, step_torch = p.astype(np.float64) - before, tp.detach().numpy().astype(np.float64) - before
+        assert np.allclose(step_ours, step_torch, rtol=1e-5, atol=1e-5 * lr)
+        if s == 1:                                              # first step: |step| = lr for ANY non-zero gradient, 1e-12-sized ones too
+            assert np.abs(step_torch).min() > 0.99 * lr and np.abs(step_ours).min() > 0.99 * lr
