@@ -5,13 +5,14 @@ import numpy as np, torch
 import bench
 from skelsplat_b200 import configs, trainer
 cfg = configs.get_config(sys.argv[1]) if len(sys.argv) > 1 else configs.H36M
-F = 2048
+F = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
+CAPS = tuple(int(c) for c in sys.argv[2].split(',')) if len(sys.argv) > 2 else (256, 320, 384, 512)
 for seed in (100, 103, 106):
     seq, host, gt = bench.make_host_batch(cfg, F, seed=seed)
     host.pop("poses_2d")
     ps = trainer.pack_sequence(cfg, seq.cameras, host["xyz"], None, "cuda", host=host)
     init = tuple(t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity))
-    for rcap in (256, 320, 384, 512):
+    for rcap in CAPS:
         ts = []
         for rep in range(2):
             for d, s_ in zip((ps.xyz, ps.scaling, ps.rotation, ps.opacity), init): d.copy_(s_)
