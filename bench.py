@@ -334,7 +334,7 @@ def run_ours(args):
         "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "setup_gpu": setup, "dense_surface": dense_ctx, "cpu_baseline": cpu,
         "accuracy": {"mpjpe_init_mm": round(mpjpe(host["xyz"], gt), 3), "mpjpe_final_mm": round(mpjpe(final, gt), 3)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -539,10 +539,30 @@ def run_reference(args):
                              "device": dev},
             "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG=VERSION is set in the environment), so the real stdout is kept for the result line and fd 1 is pointed at
+    stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
