@@ -105,6 +105,9 @@ def camera_tensors(cams, device):
 
 
 def pack_sequence(cfg: SceneConfig, cams, poses_init, poses_2d, device="cuda", host=None) -> PackedSequence:
+    """Upload a host-prepared batch (pack_host: numpy heatmap ROIs, the readable specification of the setup and the route for
+    callers that already hold heatmaps on the host).  The production route prepares everything on the GPU instead:
+    setup_gpu.pack_sequence_gpu / StreamingOptimizer.submit_detections.  Either way the optimisation itself has no CPU path."""
     host = pack_host(cfg, cams, poses_init, poses_2d) if host is None else host
     vm, pm, dims, tanfov = camera_tensors(cams, device)
     t = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
