@@ -104,3 +104,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(lib.SkelSplatLibraryError):
         lib.lib()
+
+
+def test_fill_kernel_uses_256_bit_stores_and_library_is_sm_100a():
+    """SASS evidence for two DESIGN claims: the zero fill streams with STG.E.256 (new on sm_100) and the library carries
+    sm_100a code only."""
+    import shutil
+    import subprocess
+    from skelsplat_b200 import lib
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3ssb16fill_zero_kernelE11ssb_camerasiPfPKlS1_S3_", lib.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    if "STG" not in sass:                                       # mangled name changed: fall back to the whole library
+        sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert ".256" in sass and "STG.E" in sass
