@@ -274,3 +274,24 @@ def test_adam_mirror_matches_torch_adam():
         assert np.allclose(step_ours, step_torch, rtol=1e-5, atol=1e-5 * lr)
         if s == 1:                                              # first step: |step| = lr for ANY non-zero gradient, 1e-12-sized ones too
             assert np.abs(step_torch).min() > 0.99 * lr and np.abs(step_ours).min() > 0.99 * lr
+
+
+def test_closed_form_sorted_positions_on_random_rectangles():
+    """Same property without a renderer: for arbitrary tile rectangles (empty, 1 x N, nested, identical, disjoint) and depths with
+    ties, the closed form equals a stable sort of the emitted pairs by (tile id, depth bits)."""
+    from skelsplat_b200 import binning
+    rng = np.random.default_rng(7)
+    gx = 40
+    for trial in range(60):
+        P = int(rng.integers(1, 21))
+        x0 = rng.integers(0, gx - 1, P); y0 = rng.integers(0, 30, P)
+        w = rng.integers(0, 7, P); h = rng.integers(0, 7, P)                 # zero width / height: touches no tile
+        rects = np.stack([x0, y0, np.minimum(x0 + w, gx), y0 + h], 1)
+        rects[(w == 0) | (h == 0)] = 0
+        if trial % 3 == 0 and P > 2:
+            rects[1] = rects[0]                                               # identical footprints
+        depth = rng.integers(0, 4, P).astype(np.uint32) * 1000 + 0x3F800000   # many equal depths
+        gs, xy, pos = binning.sorted_positions(rects, depth)
+        keys = (xy[:, 1] * gx + xy[:, 0]).astype(np.int64) * (1 << 32) + depth[gs].astype(np.int64)
+        expect = np.argsort(keys, kind="stable")                              # emission order breaks ties, as the radix sort does
+        assert np.array_equal(np.argsort(pos), expect)
