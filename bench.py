@@ -26,8 +26,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "h36m.yaml SkelSplat per-frame optimisation, 17 joint Gaussians x 4 views (1002x1000,1000x1000,1000x1000,1002x1000), 500 iterations, synthetic heatmaps"
-N_DISTINCT = 64          # distinct synthetic frames generated on the host; replicated (data included) to F
+CONFIG_CHOICES = ("h36m", "h36m-occ", "panoptic", "occlusion-person-8v")     # BASELINE.json configs 2-5
+SEED = 100               # camera rig + (shard 0) frames; the reference arm optimises frames of the same sequence
+N_DISTINCT = 256         # distinct synthetic frames generated per rank; replicated to F frames per step
+SWEEP_FRAMES = {"occlusion-person-8v": 100_000}     # BASELINE config 5: 100k-frame batched throughput sweep (total over ranks)
+
+
+def workload(cfg):
+    sizes = ",".join(f"{w}x{h}" for w, h in cfg.image_sizes[:cfg.nviews])
+    occ = ", occluded detections (2-3 joints x 1-2 views replaced by 40 px outliers)" if cfg.occluded else ""
+    yaml = cfg.name + ".yaml" + (f" ({cfg.nviews}-view sweep)" if cfg.name == "occlusion-person" and cfg.nviews != 4 else "")
+    return (f"{yaml} SkelSplat per-frame optimisation, {cfg.n_joints} joint Gaussians x {cfg.nviews} views ({sizes}), "
+            f"{cfg.iterations} iterations, synthetic heatmaps{occ}")
+
+
+def ref_pose_file(name):
+    """Hand-over between the two arms (the driver runs `--impl reference` first, then ours, on the same box): the reference
+    arm leaves the final poses of the frames it optimised here; our arm optimises the same frames and reports the deviation."""
+    import tempfile
+    return os.path.join(tempfile.gettempdir(), f"skelsplat_b200_refposes_{name}.npz")
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -117,74 +134,115 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- data
-def make_host_batch(cfg, F, seed):
-    """F frames of one synthetic sequence as pinned-memory-ready numpy arrays (ROI data replicated per frame)."""
-    from skelsplat_b200 import synthetic, trainer
-    seq = synthetic.make_sequence(cfg, min(F, N_DISTINCT), seed=seed)
-    poses_init = np.stack([f.pose_3d_init for f in seq.frames]); poses_2d = np.stack([f.poses_2d for f in seq.frames])
-    host = trainer.pack_host(cfg, seq.cameras, poses_init, poses_2d)
-    n0 = poses_init.shape[0]
+def make_detection_batch(cfg, F, rank):
+    """F frames of ONE synthetic sequence (one camera rig, seed SEED; rank r optimises shard r of it): detections + DLT
+    initial guess, what a user of the reference holds on the host per frame.  N_DISTINCT distinct frames, replicated to F."""
+    from skelsplat_b200 import synthetic
+    n0 = min(F, N_DISTINCT)
+    seq = synthetic.make_sequence(cfg, n0, seed=SEED, shard=rank)
     reps = (F + n0 - 1) // n0
-    per = host["roi_data"].size
-    out = {}
-    for k in ("xyz", "scaling", "rotation", "opacity", "roi_rect"):
-        out[k] = np.ascontiguousarray(np.concatenate([host[k]] * reps)[:F])
-    out["roi_offset"] = np.ascontiguousarray(np.concatenate([host["roi_offset"] + r * per for r in range(reps)])[:F])
-    out["roi_data"] = np.ascontiguousarray(np.concatenate([host["roi_data"]] * reps))
-    gt = np.concatenate([np.stack([f.pose_3d_gt for f in seq.frames])] * reps)[:F]
-    out["poses_2d"] = np.ascontiguousarray(np.concatenate([poses_2d.astype(np.float32)] * reps)[:F])   # detections (e2e input)
-    return seq, out, gt
+    rep = lambda a: np.ascontiguousarray(np.concatenate([a] * reps)[:F])
+    p2d = rep(np.stack([f.poses_2d for f in seq.frames]).astype(np.float32))
+    init = rep(np.stack([f.pose_3d_init for f in seq.frames]).astype(np.float32))
+    gt = rep(np.stack([f.pose_3d_gt for f in seq.frames]))
+    return seq, p2d, init, gt
 
 
-def n_mask_total(cfg, seq, host, F):
-    """Algorithmic bytes need N_mask (the reference's loss-mask size, utils/loss_utils.py:88-97) per view-iteration;
-    estimated on the host from the GT windows (|gt>0|) -- a lower bound of the true mask (render>0 outside the window adds ~10%)."""
-    n = 0
-    rect = host["roi_rect"][:min(F, N_DISTINCT)]
-    return float((rect[..., 2] * rect[..., 3]).sum()) / (rect.shape[0] * rect.shape[1])   # per view
+def measure_n_mask(torch, cfg, seq, dev, frames=4):
+    """N_mask of SURVEY 8(d) R2 -- |(gt > 0) | (render > 0)| summed over channels, the denominator the reference's loss computes
+    (utils/loss_utils.py:88-97) -- MEASURED with the dense op at the initial state, mean per view over `frames` frames."""
+    from skelsplat_b200 import heatmaps, trainer
+    from skelsplat_b200 import rasterizer as R
+    J = cfg.n_joints
+    tot, n = 0, 0
+    for fr in seq.frames[:frames]:
+        xyz0, scal0, rot0, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+        rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal0[0], rot0[0])
+        means = torch.from_numpy(xyz0).to(dev); scales = torch.exp(torch.from_numpy(scal0).to(dev)); rots = torch.from_numpy(rot0).to(dev)
+        for v, cam in enumerate(seq.cameras):
+            gt = torch.from_numpy(heatmaps.rois_to_dense(rois, v)).to(dev)
+            color, _, _, _ = R.rasterize_batched(means, scales, rots, torch.ones(1, J, device=dev), torch.eye(J, device=dev),
+                                                 torch.from_numpy(cam.world_view_transform).to(dev).reshape(1, 4, 4),
+                                                 torch.from_numpy(cam.full_proj_transform).to(dev).reshape(1, 4, 4),
+                                                 cam.image_width, cam.image_height, cam.tanfovx, cam.tanfovy, render_invdepth=False)
+            tot += int(((gt > 0) | (color[0] > 0)).sum().item()); n += 1
+    return tot / n
 
 
 # ----------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from skelsplat_b200 import configs, trainer, lib as L
-    from skelsplat_b200 import rasterizer as R
-
-    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
+def timed(torch, dist, fn, steps, warmup, world, dev, launches, sampler=None, streams=()):
+    """W untimed + K timed steps bracketed by barrier + synchronize; CUDA events on the current stream; max over ranks."""
+    if sampler:
+        sampler.start()
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-    cfg = configs.H36M
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = launches[0]
+    if sampler:
+        sampler.begin()
+    e0.record()
+    for st in streams:                                   # side streams start after e0 ...
+        st.wait_stream(torch.cuda.current_stream())
+    for _ in range(steps):
+        fn()
+    for st in streams:                                   # ... and e1 is recorded after everything they did
+        torch.cuda.current_stream().wait_stream(st)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_local = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    ms = ms_local
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, launches[0] - l0, clocks, ms_local
+
+
+def measure_config(torch, dist, name, args, rank, world, local, headline):
+    """One BASELINE config on this rank's GPU: resident throughput, kernel-only roofline, e2e through the public streaming API.
+    Returns the dict of results (rank 0 assembles the line); collective calls inside are made by every rank."""
+    from skelsplat_b200 import configs, trainer, setup_gpu, lib as L
+    cfg = configs.get_config(name)
+    dev = f"cuda:{local}"
     F = args.frames
-    seq, host, gt = make_host_batch(cfg, F, seed=100 + rank)      # each rank optimises its own shard of the sequence
-    det_host = {"poses_2d": torch.from_numpy(host.pop("poses_2d")).pin_memory()}
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
-    det_host["xyz"] = pinned["xyz"]
-    ps = trainer.pack_sequence(cfg, seq.cameras, host["xyz"], None, dev, host=host)
-    init = tuple(t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity))
+    steps = args.steps
+    if name in SWEEP_FRAMES and not headline:
+        steps = max(args.steps, -(-SWEEP_FRAMES[name] // (world * F)))      # the 100k-frame sweep: total frames over all ranks
+    seq, p2d, init, gt = make_detection_batch(cfg, F, rank)
+    det_host = {"poses_2d": torch.from_numpy(p2d).pin_memory(), "xyz": torch.from_numpy(init).pin_memory()}
+    # resident inputs: initial state + GT heatmap ROIs produced on the GPU from the detections (setup_gpu; the windows are
+    # identical to the host specification's, tests/test_gpu_setup.py)
+    ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, det_host["poses_2d"], det_host["xyz"], dev)
+    roi_floats = int(ps.roi_data.numel())
+    init_state = tuple(t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity))
     gathered = torch.empty((world * F, cfg.n_joints, 3), dtype=torch.float32, device=dev) if world > 1 else None
     launches = [0]
+    rcap = trainer.default_r_capacity(cfg)
 
     def reset():
-        for dst, src in zip((ps.xyz, ps.scaling, ps.rotation, ps.opacity), init):
+        for dst, src in zip((ps.xyz, ps.scaling, ps.rotation, ps.opacity), init_state):
             dst.copy_(src)
 
-    def step_resident():
+    def step_resident(collective=True):
         reset()
         trainer.optimize_packed(ps, check=False)
         launches[0] += 1
-        if world > 1:
+        if world > 1 and collective:
             dist.all_gather_into_tensor(gathered, ps.xyz)
 
     # e2e: the public streaming API -- every step copies that step's inputs from pinned host memory and reads the poses back;
-    # the copy of step i+1 overlaps the optimisation of step i (double-buffered)
-    # Two forms: (1) detections in -> poses out (the e2e headline): a step's host inputs are what a user of the reference has
-    # on the host -- 2D detections + the initial 3D guess -- and the GT heatmap ROIs are generated on the GPU inside the timed
-    # region (the reference also builds its heatmaps on the GPU from the detections, utils/general_utils.py:175-304);
-    # (2) ROI streaming: host-prepared heatmap patches cross PCIe every step (841 MB/step), reported as e2e_roi_streaming.
-    so = trainer.StreamingOptimizer(cfg, seq.cameras, F, int(pinned["roi_data"].numel() * 1.1), dev)
+    # the copy of step i+1 overlaps the optimisation of step i (double-buffered).  Host inputs of a step = what a user of the
+    # reference has on the host: 2D detections + the initial 3D guess; the GT heatmap ROIs are generated on the GPU inside
+    # the timed region (the reference also builds its heatmaps on the GPU from the detections, utils/general_utils.py:175-304).
+    so = trainer.StreamingOptimizer(cfg, seq.cameras, F, int(roi_floats * 1.1), dev)
     tickets = []
 
     def make_step_e2e(submit, arg):
@@ -197,70 +255,132 @@ def run_ours(args):
             if len(tickets) >= 2:
                 so.result(tickets[-2])                  # poses of the previous batch are on the host before the next submit
         return step
-    step_e2e = make_step_e2e(so.submit_detections, det_host)
-    step_e2e_roi = make_step_e2e(so.submit, pinned)
 
-    def timed(fn, steps, warmup, sample_clocks=False, streams=()):
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = launches[0]
-        if sampler:
-            sampler.begin()
-        e0.record()
-        for st in streams:                                   # side streams start after e0 ...
-            st.wait_stream(torch.cuda.current_stream())
-        for _ in range(steps):
-            fn()
-        for st in streams:                                   # ... and e1 is recorded after everything they did
-            torch.cuda.current_stream().wait_stream(st)
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches[0] - l0, clocks
-
-    ms, n_launch, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    sampler = ClockSampler(local) if headline else None
+    ms, n_launch, clocks, ms_local = timed(torch, dist, step_resident, steps, args.warmup, world, dev, launches, sampler)
     # kernel-only duration for the roofline (same stream, CUDA events around the launch alone)
     reset(); torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    oc_k = trainer.make_opt_config(cfg, trainer.default_r_capacity(cfg))
+    oc_k = trainer.make_opt_config(cfg, rcap)
     lr_k = trainer.xyz_lr_table(cfg, ps.spatial_lr_scale, oc_k.iterations)
     loss_k = torch.empty(F, dtype=torch.float32, device=dev)
     k0.record(); status_k = trainer._launch(ps, oc_k, lr_k, loss_k); k1.record(); torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1)
+    final = ps.xyz.cpu().numpy()
     n_over_t = (status_k != 0).sum().to(torch.int64).reshape(1)       # frames that outgrew r_capacity (they need the retry path): must be 0
+    diag = None
     if world > 1:
         dist.all_reduce(n_over_t)
+        # scaling diagnostics: per-rank kernel time, the step without the collective, the collective alone
+        kt = torch.tensor([kernel_ms, ms_local / steps], device=dev); kall = torch.empty((world, 2), device=dev)
+        dist.all_gather_into_tensor(kall, kt)
+        ms_nc, _, _, _ = timed(torch, dist, lambda: step_resident(False), steps, 1, world, dev, launches)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); dist.barrier(); g0.record()
+        for _ in range(20):
+            dist.all_gather_into_tensor(gathered, ps.xyz)
+        g1.record(); torch.cuda.synchronize()
+        kl = kall.cpu().numpy()
+        diag = {"kernel_ms_per_rank": [round(float(x), 3) for x in kl[:, 0]], "step_ms_per_rank_local": [round(float(x), 3) for x in kl[:, 1]],
+                "step_ms_without_collective": round(ms_nc / steps, 3), "all_gather_ms": round(g0.elapsed_time(g1) / 20, 4)}
     n_overflowed = int(n_over_t.item())
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, streams=(so.copy_stream, so.compute_stream))
+    ms_e2e, _, _, _ = timed(torch, dist, make_step_e2e(so.submit_detections, det_host), steps, args.warmup, world, dev, launches,
+                            streams=(so.copy_stream, so.compute_stream))
     final_e2e = so.result(tickets[-1])
     del tickets[:]
-    ms_e2e_roi, _, _ = timed(step_e2e_roi, args.steps, args.warmup, streams=(so.copy_stream, so.compute_stream))
-    so.result(tickets[-1])
-    final = ps.xyz.cpu().numpy()
-
     total_frames = world * F
-    value = total_frames * args.steps / (ms / 1e3)
-    e2e_value = total_frames * args.steps / (ms_e2e / 1e3)
     h2d = sum(int(v.numel() * v.element_size()) for v in det_host.values())
-    h2d_roi = sum(int(v.numel() * v.element_size()) for v in pinned.values())
     d2h = int(F * cfg.n_joints * 3 * 4 + F * 4)          # final poses + per-frame status words
+    out = {"cfg": cfg, "name": name, "seq": seq, "gt": gt, "init": init, "steps": steps, "ms": ms, "n_launch": n_launch, "clocks": clocks,
+           "kernel_ms": kernel_ms, "n_overflowed": n_overflowed, "diag": diag, "value": total_frames * steps / (ms / 1e3),
+           "e2e_value": total_frames * steps / (ms_e2e / 1e3), "ms_e2e": ms_e2e, "h2d": h2d, "d2h": d2h, "final": final,
+           "final_e2e": final_e2e, "roi_floats": roi_floats, "rcap": rcap, "F": F}
+    if headline:
+        # ROI streaming form: host-prepared heatmap patches cross PCIe every step
+        pinned = {k: getattr(ps, k).cpu().pin_memory() for k in ("roi_rect", "roi_offset", "roi_data")}
+        for k, t in zip(("xyz", "scaling", "rotation", "opacity"), init_state):
+            pinned[k] = t.cpu().pin_memory()
+        ms_roi, _, _, _ = timed(torch, dist, make_step_e2e(so.submit, pinned), steps, args.warmup, world, dev, launches,
+                                streams=(so.copy_stream, so.compute_stream))
+        so.result(tickets[-1])
+        out["e2e_roi"] = {"value": round(total_frames * steps / (ms_roi / 1e3), 2), "unit": "frames/s",
+                          "h2d_bytes_per_step": sum(int(v.numel() * v.element_size()) for v in pinned.values()), "d2h_bytes_per_step": d2h,
+                          "ms_per_step": round(ms_roi / steps, 3),
+                          "includes": "trainer.StreamingOptimizer.submit: host-prepared GT heatmap ROI patches + initial state cross PCIe every step"}
+    del so, ps, gathered
+    torch.cuda.empty_cache()
+    return out
 
+
+def roofline_of(torch, m, dev, hbm_peak, peak_src, traffic):
+    """HBM roofline of the fused optimiser launch (R2): algorithmic bytes = (4 N_mask + 100 J) per view-iteration,
+    N_mask measured with the dense op; duration = the live CUDA-event time of the launch alone."""
+    cfg, F = m["cfg"], m["F"]
+    nmask_view = measure_n_mask(torch, cfg, m["seq"], dev)
+    bytes_view_iter = 4.0 * nmask_view + 100.0 * cfg.n_joints
+    bytes_launch = bytes_view_iter * cfg.iterations * F
+    achieved = bytes_launch / (m["kernel_ms"] / 1e3) / 1e9
+    r = {"kernel": f"optimize_kernel<{cfg.accumulation_steps}> (fused per-frame optimiser, R2)", "bound": "hbm", "achieved": round(achieved, 2),
+         "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None,
+         "algorithmic_bytes_per_launch": round(bytes_launch), "n_mask_per_view_measured": round(nmask_view, 1),
+         "algorithmic_bytes_per_view_iteration": round(bytes_view_iter, 1), "kernel_ms": round(m["kernel_ms"], 3), "peak_source": peak_src}
+    t = traffic.get("optimize_kernel", {}).get(m["name"]) if traffic else None
+    if t:       # ncu-captured constants: only valid for the library build they were captured from
+        scale = F / t["frames_in_capture"]
+        r["traffic"] = round((t["dram_bytes_read"] + t["dram_bytes_write"]) * scale)
+        r["issue_slot_utilisation_ncu"] = t["issue_active_pct"] / 100.0
+        inst = t["inst_executed"] * scale / (m["kernel_ms"] / 1e3) / 1e9
+        r["issue_roofline"] = {"bound": "issue-slots", "unit": "G warp-inst/s", "achieved": round(inst, 1), "peak": round(148 * 4 * 1.965, 1),
+                               "peak_source": "148 SMs x 4 issue slots/clk x 1.965 GHz (clocks.max.sm)", "frac": round(inst / (148 * 4 * 1.965), 4)}
+        r["ncu_source"] = t.get("source")
+    return r
+
+
+def accuracy_vs_reference(torch, cfg, name, dev):
+    """The reference arm (run first by the driver) leaves the final poses of the frames it optimised; optimise the SAME frames
+    with the fused kernel and report the deviation.  None when the file is absent (reference arm not run on this box)."""
+    from skelsplat_b200 import synthetic, trainer
+    path = ref_pose_file(name)
+    if not os.path.exists(path):
+        return None
+    G = np.load(path)
+    idx = [int(i) for i in G["frame_indices"]]
+    seq = synthetic.make_sequence(cfg, max(idx) + 1, seed=int(G["seed"]))
+    sub = synthetic.Sequence(cfg=cfg, cameras=seq.cameras, frames=[seq.frames[i] for i in idx])
+    if not np.allclose(np.stack([f.pose_3d_init for f in sub.frames]), G["init_xyz"]):
+        return {"error": "reference pose file was made from different synthetic inputs"}
+    mine = trainer.optimize_sequence(sub, dev, iterations=int(G["iterations"]))
+    ref, gt = G["ref_xyz"], np.stack([f.pose_3d_gt for f in sub.frames])
+    dev_mm = np.linalg.norm(mine - ref, axis=-1)
+    return {"frames": len(idx), "iterations": int(G["iterations"]), "vs_reference_max_mm": round(float(dev_mm.max()), 4),
+            "vs_reference_median_mm": round(float(np.median(dev_mm)), 5),
+            "mpjpe_ours_mm": round(trainer.mpjpe(mine, gt), 4), "mpjpe_reference_mm": round(trainer.mpjpe(ref, gt), 4),
+            "mpjpe_delta_mm": round(trainer.mpjpe(mine, gt) - trainer.mpjpe(ref, gt), 4),
+            "mpjpe_init_mm": round(trainer.mpjpe(G["init_xyz"], gt), 4),
+            "note": "same frames as `bench.py --impl reference` optimised on this box (unmodified reference kernels, real torch Adam); "
+                    "the reference's own run-to-run spread (unordered fp32 atomics + Adam eps=1e-15) is 0.2-0.5 mm per joint on the h36m configs"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from skelsplat_b200 import configs, trainer, lib as L
+    from skelsplat_b200 import rasterizer as R
+    from skelsplat_b200.trainer import mpjpe
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    main = measure_config(torch, dist, args.config, args, rank, world, local, headline=True)
+    extra_names = [n for n in CONFIG_CHOICES if n != args.config] if args.configs == "all" else []
+    extras = {}
+    for n in extra_names:
+        try:
+            extras[n] = measure_config(torch, dist, n, args, rank, world, local, headline=False)
+        except Exception as e:      # noqa: BLE001 -- must fail on every rank alike (deterministic errors only); keep the headline
+            extras[n] = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -273,67 +393,71 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    # ncu-derived constants (DRAM traffic, executed instructions) are tied to the build they were captured from: they are
+    # used only when the loaded library's source hash matches the one recorded with them
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if t.get("source_hash") == L.lib().ssb_source_hash().decode():
+            traffic = t
     except Exception:
         pass
-    nmask_view = n_mask_total(cfg, seq, host, F)
-    bytes_view_iter = 4.0 * nmask_view + 100.0 * cfg.n_joints               # R2, SURVEY.md 8d
-    bytes_launch = bytes_view_iter * cfg.iterations * F
-    achieved = bytes_launch / (kernel_ms / 1e3) / 1e9
-    roofline = {"kernel": "optimize_kernel<4> (fused per-frame optimiser, R2)", "bound": "hbm", "achieved": round(achieved, 2),
-                "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 5),
-                "traffic": (round((traffic["optimize_kernel"]["dram_bytes_read"] + traffic["optimize_kernel"]["dram_bytes_write"]) * F
-                                  / traffic["optimize_kernel"]["frames_in_capture"]) if "optimize_kernel" in traffic else None),
-                "algorithmic_bytes_per_launch": round(bytes_launch),
-                "issue_slot_utilisation_ncu": (traffic["optimize_kernel"]["issue_active_pct"] / 100.0 if "optimize_kernel" in traffic else None),
-                # the roof that actually binds this kernel: warp-instruction issue slots (148 SMs x 4 schedulers x SM clock).  Executed
-                # instructions per frame come from the committed ncu capture (data-dependent only through the synthetic seed); the
-                # duration is this run's.
-                "issue_roofline": ({"bound": "issue-slots", "unit": "G warp-inst/s",
-                                    "achieved": round(traffic["optimize_kernel"]["inst_executed"] * F / traffic["optimize_kernel"]["frames_in_capture"]
-                                                      / (kernel_ms / 1e3) / 1e9, 1),
-                                    "peak": round(148 * 4 * 1.965, 1), "peak_source": "148 SMs x 4 issue slots/clk x 1.965 GHz (clocks.max.sm)",
-                                    "frac": round(traffic["optimize_kernel"]["inst_executed"] * F / traffic["optimize_kernel"]["frames_in_capture"]
-                                                  / (kernel_ms / 1e3) / 1e9 / (148 * 4 * 1.965), 4)}
-                                   if "inst_executed" in traffic.get("optimize_kernel", {}) else None),
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_view_iteration": round(bytes_view_iter, 1), "kernel_ms": round(kernel_ms, 3),
-                "note": "R2 is issue-slot/MUFU bound, not HBM bound (SURVEY.md 8d): see profiles/ for issue-slot utilisation; "
-                        "the HBM-roofline op is the dense rasteriser in m2_rasterizer_dense"}
+
     def guarded(fn, *a):          # the secondary blocks must never cost the headline line
         try:
             return fn(*a)
         except Exception as e:    # noqa: BLE001
             return {"error": repr(e)[:300]}
+
+    def cfg_block(m, name):
+        cfg = m["cfg"]
+        blk = {"workload": workload(cfg), "value": round(m["value"], 2), "unit": "frames/s", "ms_per_step": round(m["ms"] / m["steps"], 3),
+               "steps": m["steps"], "frames_per_gpu_per_step": m["F"], "total_frames_timed": m["F"] * world * m["steps"],
+               "r_capacity": m["rcap"], "frames_over_capacity_all_ranks": m["n_overflowed"],
+               "e2e": {"value": round(m["e2e_value"], 2), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                       "ms_per_step": round(m["ms_e2e"] / m["steps"], 3), "mpjpe_mm": round(mpjpe(m["final_e2e"], m["gt"]), 3)},
+               "roofline": guarded(roofline_of, torch, m, dev, hbm_peak, peak_src, traffic),
+               "accuracy": {"mpjpe_init_mm": round(mpjpe(m["init"], m["gt"]), 3), "mpjpe_final_mm": round(mpjpe(m["final"], m["gt"]), 3),
+                            "vs_reference": guarded(accuracy_vs_reference, torch, cfg, name, dev)},
+               "roi_mb_per_step": round(m["roi_floats"] * 4 / 1e6, 1)}
+        if m["diag"]:
+            blk["scaling_diag"] = m["diag"]
+        return blk
+
+    mb = cfg_block(main, args.config)
+    cfg, seq, F = main["cfg"], main["seq"], main["F"]
     m2 = guarded(bench_dense_rasterizer, torch, R, cfg, seq, dev, hbm_peak) if world == 1 else None
     if m2 and "roofline" in m2 and "dense_rasterizer" in traffic:
         t = traffic["dense_rasterizer"]
         m2["roofline"]["traffic"] = round((t["dram_bytes_read"] + t["dram_bytes_write"]) / t["views_in_capture"] * m2["views_per_launch"])
         m2["roofline"]["algorithmic_bytes_per_launch"] = m2["roofline"]["algorithmic_bytes_per_view"] * m2["views_per_launch"]
-    cpu = guarded(cpu_baseline, cfg, seq) if world == 1 else None
+    cpu = guarded(cpu_baseline, cfg, seq, dev) if world == 1 else None
     setup = guarded(bench_setup, torch, cfg, seq, dev) if world == 1 else None
     dense_ctx = guarded(bench_dropin_and_losses, torch, cfg, seq, dev, hbm_peak) if world == 1 else None
-    from skelsplat_b200.trainer import mpjpe
     line = {
-        "metric": "optimised_frames_per_sec", "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "metric": "optimised_frames_per_sec", "value": mb["value"], "unit": "frames/s", "n_gpus": world, "steps": main["steps"],
+        "warmup": args.warmup, "ms_per_step": mb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": F, "r_capacity": trainer.default_r_capacity(cfg), "frames_over_capacity_all_ranks": n_overflowed, "iterations": cfg.iterations, "adam_steps": cfg.iterations // cfg.accumulation_steps,
-                   "loss": "l2_gaussian + 1e-5 limb consistency", "parallelism": f"frame-sharded x{world}" + (", NCCL all_gather of final poses" if world > 1 else ""),
-                   "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)"},
-        "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e / args.steps, 3), "mpjpe_mm": round(trainer.mpjpe(final_e2e, gt), 3),
-                "includes": "trainer.StreamingOptimizer.submit_detections: per step pinned-host -> device copy of the 2D detections + initial 3D guess, "
-                            "initial Gaussian state and GT heatmap ROIs generated on the GPU (ssb_heatmap_roi_*), fused optimiser, device -> host copy "
-                            "of final poses + status words; the copies of step i+1 overlap the kernels of step i"},
-        "e2e_roi_streaming": {"value": round(total_frames * args.steps / (ms_e2e_roi / 1e3), 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_roi,
-                              "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e_roi / args.steps, 3),
-                              "includes": "trainer.StreamingOptimizer.submit: host-prepared GT heatmap ROI patches + initial state cross PCIe every step"},
-        "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "m2_rasterizer_dense": m2, "setup_gpu": setup, "dense_surface": dense_ctx, "cpu_baseline": cpu,
-        "accuracy": {"mpjpe_init_mm": round(mpjpe(host["xyz"], gt), 3), "mpjpe_final_mm": round(mpjpe(final, gt), 3)},
+        "config": {"workload": mb["workload"], "name": args.config, "frames_per_gpu_per_step": F, "r_capacity": main["rcap"],
+                   "frames_over_capacity_all_ranks": main["n_overflowed"], "iterations": cfg.iterations,
+                   "adam_steps": cfg.iterations // cfg.accumulation_steps, "loss": "l2_gaussian + 1e-5 limb consistency",
+                   "parallelism": f"frame-sharded x{world} (shards of one sequence, one camera rig)" + (", NCCL all_gather of final poses" if world > 1 else ""),
+                   "l2": f"inputs larger than L2: {mb['roi_mb_per_step']:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)",
+                   "library": {"ssb_version": int(L.lib().ssb_version()), "source_hash": L.lib().ssb_source_hash().decode()}},
+        "e2e": dict(mb["e2e"], includes="trainer.StreamingOptimizer.submit_detections: per step pinned-host -> device copy of the 2D detections + "
+                    "initial 3D guess, initial Gaussian state and GT heatmap ROIs generated on the GPU (ssb_heatmap_roi_*), fused optimiser, "
+                    "device -> host copy of final poses + status words; the copies of step i+1 overlap the kernels of step i"),
+        "e2e_roi_streaming": main.get("e2e_roi"),
+        "gpu_launches": main["n_launch"], "clocks": main["clocks"],
+        "roofline": dict(mb["roofline"], note="R2 is issue-slot/MUFU bound, not HBM bound (SURVEY.md 8d): see profiles/ for issue-slot utilisation; "
+                         "the HBM-roofline op is the dense rasteriser in m2_rasterizer_dense") if "error" not in mb["roofline"] else mb["roofline"],
+        "m2_rasterizer_dense": m2, "setup_gpu": setup, "dense_surface": dense_ctx, "cpu_baseline": cpu,
+        "accuracy": mb["accuracy"],
+        # the other BASELINE configs, measured in this same run at N = world size (same warm-up; the 8-view sweep runs 100k frames)
+        "configs": {n: (cfg_block(m, n) if "error" not in m else m) for n, m in extras.items()},
     }
+    if main["diag"]:
+        line["scaling_diag"] = main["diag"]
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -456,12 +580,15 @@ def bench_dropin_and_losses(torch, cfg, seq, dev, hbm_peak):
 
 
 # ----------------------------------------------------------------------------------------- CPU baseline
-def cpu_baseline(cfg, seq, budget_s=12.0):
-    """Oracle port on the box's host cores: DLT initialisation + C-oracle forward/backward + torch-CPU loss of one
-    view-iteration (the same restated loop the parity tests use), on a bounded sample."""
+def cpu_baseline(cfg, seq, dev=None, repeats=5, iters=4, check_frames=8, check_iters=16):
+    """Oracle port on the box's host cores (SURVEY.md 8d protocol, bounded): (i) DLT initialisation frames/s; (ii) one
+    view-iteration = C-oracle rasteriser fwd+bwd + torch-CPU dense loss / autograd / Adam in the restated train.py loop:
+    3 warm-up runs, median of `repeats` timed runs of `iters` iterations, extrapolated x500 to frames/s; (iii) `check_frames`
+    frames x `check_iters` iterations end to end on the CPU, cross-checked (max joint deviation, MPJPE) against the fused GPU
+    optimiser run for the same number of iterations."""
     import torch
     from oracle import pipeline as opipe
-    from skelsplat_b200 import heatmaps, trainer
+    from skelsplat_b200 import heatmaps, trainer, synthetic
     from skelsplat_b200.cameras import cameras_extent
     from skelsplat_b200.triangulation import triangulate_poses
     cores = os.cpu_count()
@@ -471,37 +598,53 @@ def cpu_baseline(cfg, seq, budget_s=12.0):
         for f in seq.frames[:16]:
             triangulate_poses(P_list, f.poses_2d); n += 1
     dlt_fps = n / (time.perf_counter() - t0)
+    ext = cameras_extent(seq.cameras)
+
+    def dense_gt(fr):
+        _, scal0, rot0, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+        rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal0[0], rot0[0])
+        return [torch.from_numpy(heatmaps.rois_to_dense(rois, v)) for v in range(cfg.nviews)]
     fr = seq.frames[0]
-    xyz0, scal0, rot0, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
-    rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal0[0], rot0[0])
-    dense = [torch.from_numpy(heatmaps.rois_to_dense(rois, v)) for v in range(cfg.nviews)]
-    iters = 4
-    opipe.optimise_frame(fr, seq.cameras, cfg, cameras_extent(seq.cameras), dense, backend="oracle", device="cpu", iterations=iters)  # warm-up
-    t0 = time.perf_counter(); done = 0
-    while time.perf_counter() - t0 < budget_s:
-        opipe.optimise_frame(fr, seq.cameras, cfg, cameras_extent(seq.cameras), dense, backend="oracle", device="cpu", iterations=iters)
-        done += iters
-    vi_per_s = done / (time.perf_counter() - t0)
+    dense = dense_gt(fr)
+    run = lambda n_it: opipe.optimise_frame(fr, seq.cameras, cfg, ext, dense, backend="oracle", device="cpu", iterations=n_it)
+    for _ in range(3):
+        run(iters)
+    ts = []
+    for _ in range(repeats):
+        t0 = time.perf_counter(); run(iters); ts.append((time.perf_counter() - t0) / iters)
+    vi_per_s = 1.0 / float(np.median(ts))
+    # end-to-end cross-check on `check_frames` frames (bounded to check_iters iterations: 500 would take ~5 min of CPU)
+    frames = seq.frames[:check_frames]
+    t0 = time.perf_counter()
+    cpu_xyz = np.stack([opipe.optimise_frame(f, seq.cameras, cfg, ext, dense_gt(f), backend="oracle", device="cpu", iterations=check_iters) for f in frames])
+    e2e_s = time.perf_counter() - t0
+    check = None
+    if dev is not None:
+        gpu_xyz = trainer.optimize_sequence(synthetic.Sequence(cfg=cfg, cameras=seq.cameras, frames=frames), dev, iterations=check_iters)
+        gt = np.stack([f.pose_3d_gt for f in frames])
+        check = {"frames": len(frames), "iterations": check_iters, "max_joint_deviation_mm": round(float(np.linalg.norm(gpu_xyz - cpu_xyz, axis=-1).max()), 5),
+                 "mpjpe_cpu_mm": round(trainer.mpjpe(cpu_xyz, gt), 4), "mpjpe_gpu_mm": round(trainer.mpjpe(gpu_xyz, gt), 4),
+                 "cpu_seconds": round(e2e_s, 2)}
     return {"value": round(vi_per_s / cfg.iterations, 5), "unit": "frames/s", "cores": torch.get_num_threads(), "host_cores": cores, "kind": "port",
-            "sample": f"{done} view-iterations of one H36M-shaped frame (C-oracle rasteriser fwd+bwd single-threaded + torch-CPU dense loss/autograd/Adam on {torch.get_num_threads()} threads), extrapolated x{cfg.iterations}/frame",
-            "view_iterations_per_s": round(vi_per_s, 3), "dlt_init_frames_per_s": round(dlt_fps, 1)}
+            "sample": f"3 warm-ups, median of {repeats} runs x {iters} view-iterations of one {cfg.name}-shaped frame (C-oracle rasteriser fwd+bwd "
+                      f"single-threaded + torch-CPU dense loss/autograd/Adam on {torch.get_num_threads()} threads), extrapolated x{cfg.iterations}/frame; "
+                      f"plus {check_frames} frames x {check_iters} iterations end to end as an accuracy cross-check against the GPU path",
+            "view_iterations_per_s": round(vi_per_s, 3), "dlt_init_frames_per_s": round(dlt_fps, 1), "e2e_cross_check": check}
 
 
 # ----------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
-        return
-    import torch
-    from oracle import pipeline as opipe, ref_rasterizer as refr
+def reference_config(torch, name, n_warm, n_timed, rank, dev, use_ref):
+    """`n_timed` frames of config `name` through the UNMODIFIED reference kernels (oracle/_ref) under the restated train.py
+    loop with real torch.optim.Adam, one frame at a time as the reference does; returns (seconds per frame list, poses, meta)."""
+    from oracle import pipeline as opipe
     from skelsplat_b200 import configs, synthetic, heatmaps, trainer
     from skelsplat_b200.cameras import cameras_extent
-    cfg = configs.H36M
-    use_ref = refr.available("h36m")
-    dev = "cuda:0" if use_ref else "cpu"
+    cfg = configs.get_config(name)
     backend = "ref" if use_ref else "oracle"
     iters = cfg.iterations if use_ref else 8
-    seq = synthetic.make_sequence(cfg, args.steps + args.warmup, seed=100)
+    # rank 0 optimises frames of the plain seed-SEED sequence (our arm re-optimises exactly these for the accuracy
+    # cross-check); the other ranks take their shard of the same rig
+    seq = synthetic.make_sequence(cfg, n_warm + n_timed, seed=SEED, shard=None if rank == 0 else rank)
     ext = cameras_extent(seq.cameras)
 
     def one(frame):
@@ -511,35 +654,89 @@ def run_reference(args):
         if use_ref:
             torch.cuda.synchronize()
         t0 = time.perf_counter()
-        opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend=backend, device=dev, iterations=iters)
+        xyz = opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend=backend, device=dev, iterations=iters)
         if use_ref:
             torch.cuda.synchronize()
-        return time.perf_counter() - t0
+        return time.perf_counter() - t0, xyz
 
-    for f in seq.frames[:args.warmup]:
+    for f in seq.frames[:n_warm]:
         one(f)
-    sampler = ClockSampler(0)
+    res = [one(f) for f in seq.frames[n_warm:n_warm + n_timed]]
+    secs = [r[0] * (cfg.iterations / iters) for r in res]
+    if rank == 0 and use_ref:
+        try:
+            np.savez(ref_pose_file(name), seed=SEED, iterations=iters, frame_indices=np.arange(n_warm, n_warm + n_timed),
+                     ref_xyz=np.stack([r[1] for r in res]), init_xyz=np.stack([f.pose_3d_init for f in seq.frames[n_warm:n_warm + n_timed]]))
+        except OSError:
+            pass
+    return cfg, secs, iters
+
+
+def run_reference(args):
+    """Reference arm.  The reference is a CUDA program: its own forward.cu / backward.cu / rasterizer_impl.cu (oracle/_ref,
+    unmodified, sm_100a) under the restated train.py loop.  Under torchrun EVERY rank runs it on its own GPU (value = sum of the
+    ranks' frames/s), so the per-N ratio compares N GPUs with N GPUs.  Without oracle/_ref: the CPU oracle port on rank 0."""
+    import torch
+    from oracle import ref_rasterizer as refr
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    use_ref = all(refr.available(v) for v in ("h36m", "panoptic", "op"))
+    if not use_ref and rank != 0:
+        return
+    dist = None
     if use_ref:
-        sampler.start()
-        sampler.begin()
-    secs = [one(f) for f in seq.frames[args.warmup:args.warmup + args.steps]]
+        torch.cuda.set_device(local)
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}" if use_ref else "cpu"
+    n_ranks = world if use_ref else 1
+
+    def aggregate(secs):
+        """whole-job frames/s = sum over ranks of (frames / seconds); ms per frame = max over ranks of the mean."""
+        fps, ms = len(secs) / float(np.sum(secs)), float(np.mean(secs)) * 1e3
+        if dist is not None:
+            t = torch.tensor([fps, ms], device=dev, dtype=torch.float64); allt = torch.empty((world, 2), device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(allt, t)
+            a = allt.cpu().numpy()
+            return float(a[:, 0].sum()), float(a[:, 1].max()), [round(float(x), 4) for x in a[:, 0]]
+        return fps, ms, [round(fps, 4)]
+
+    sampler = ClockSampler(local)
+    if use_ref:
+        sampler.start(); sampler.begin()
+    cfg, secs, iters = reference_config(torch, args.config, args.warmup, args.steps, rank, dev, use_ref)
     clocks = sampler.stop() if use_ref else None
-    per_frame = float(np.sum(secs)) / len(secs) * (cfg.iterations / iters)
-    value = 1.0 / per_frame
+    value, ms_frame, per_rank = aggregate(secs)
+    extras = {}
+    if args.configs == "all":
+        for n in CONFIG_CHOICES:
+            if n == args.config:
+                continue
+            c2, s2, _ = reference_config(torch, n, 1, min(args.steps, 2), rank, dev, use_ref)
+            v2, m2, pr2 = aggregate(s2)
+            extras[n] = {"workload": workload(c2), "value": round(v2, 4), "unit": "frames/s", "ms_per_frame": round(m2, 2),
+                         "value_per_gpu": round(v2 / n_ranks, 4), "frames_timed_per_rank": len(s2)}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     kind = "reference" if use_ref else "port"
-    sample = (f"{len(secs)} frames x {iters} iterations, one frame per step: UNMODIFIED reference CUDA kernels (oracle/_ref, built from the reference's "
+    sample = (f"{len(secs)} frames x {iters} iterations per rank, one frame per step: UNMODIFIED reference CUDA kernels (oracle/_ref, built from the reference's "
               "forward.cu/backward.cu/rasterizer_impl.cu for sm_100a) on the GPU + the reference's torch ops (clamp, l2_gaussian, autograd, Adam) "
               "in the restated train.py loop; per-frame setup (heatmaps) excluded, as in our arm") if use_ref else \
              f"{len(secs)} frames x {iters} iterations on the CPU oracle port (oracle/_ref not loadable), extrapolated to 500"
-    line = {"impl": "reference", "metric": "optimised_frames_per_sec", "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus, "ranks_used": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(per_frame * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+    line = {"impl": "reference", "metric": "optimised_frames_per_sec", "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus,
+            "ranks_used": n_ranks, "value_per_gpu": round(value / n_ranks, 4), "value_per_rank": per_rank,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_frame, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": 1, "iterations": cfg.iterations},
+            "config": {"workload": workload(cfg), "name": args.config, "frames_per_gpu_per_step": 1, "iterations": cfg.iterations},
             "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                              "device": dev},
             "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "clocks": clocks}
+            "clocks": clocks, "configs": extras}
     emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 _RESULT_OUT = None
@@ -569,6 +766,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=2048, help="frames per GPU per step")
+    ap.add_argument("--config", default="h36m", choices=list(CONFIG_CHOICES), help="BASELINE config of the headline line")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="all: also measure the other BASELINE configs into the line's `configs` block (default); none: headline only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,7 +31,10 @@ extern "C" {
 #define SSB_STATUS_ROI_OVERFLOW 2u /* heatmap patches need more than the roi_data capacity given: patches were skipped */
 #define SSB_STATUS_ROI_TOO_WIDE 4u /* a heatmap patch is wider than 256 px (sigma > 31 px): outside the supported regime */
 
-int         ssb_version(void);              /* 101: ssb_opt_config grew max_unrolled_list; roi_fill takes a capacity */
+int         ssb_version(void);              /* 200: + ssb_optimize_frames_debug, ssb_source_hash, fp64 heatmap sigmas */
+/* Hex digest of the kernel sources the library was compiled from (skelsplat_b200/build.py passes -DSSB_SOURCE_HASH):
+ * a binding compares it with the sources it sits next to and refuses a stale build. */
+const char* ssb_source_hash(void);
 int         ssb_struct_size(int which);     /* sizeof: 0 ssb_gaussians, 1 ssb_cameras, 2 ssb_opt_config; -1 otherwise */
 const char* ssb_error_string(int code);
 const char* ssb_last_cuda_error(void);
@@ -180,6 +183,10 @@ typedef struct ssb_opt_config {
     int   antialiasing;
     int   max_unrolled_list;    /* tuning knob (same arithmetic, different fp32 summation order): tile lists of 5 Gaussians take the unrolled
                                    register-resident path (0 = default = 5) or the chunked generic path (4) */
+    int   resident_record_slots;/* tuning knob (bit-identical results): slots of a step group whose per-(tile,Gaussian) records are resident
+                                   in shared memory at once.  0 = auto: all of them when two CTAs per SM fit, else half (the tile phase then
+                                   runs twice per Adam step) when that keeps two CTAs per SM, else all in one 1024-thread CTA per SM.
+                                   accumulation_steps or accumulation_steps/2 force a choice. */
 } ssb_opt_config;
 
 /* lr_xyz_host: [iterations+1] learning rate of the xyz group at iteration i (host-computed in fp64
@@ -194,6 +201,18 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
                         float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
                         const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
                         float* final_loss, void* workspace, void* stream);
+
+/* Debug accessor for the bit-exact binning tests: the same launch, and additionally the binning state of
+ * frame dbg_frame at Adam step dbg_step is written to dbg_out (device, int32).  Per slot k (= iteration k of the step group)
+ * 4 + 4*r_capacity words:  R, active tiles, view, status | point_list[r_capacity] (sorted Gaussian ids, the reference's
+ * binningState.point_list, rasterizer_impl.cu:303-311) | inv_pos[r_capacity] (sorted position of each emission index) |
+ * tile[r_capacity] ((y << 8) | x of each active tile, row-major order) | start[r_capacity] (first list entry of each active
+ * tile = ranges[tile].x, rasterizer_impl.cu:116-138); unused entries are -1. */
+int ssb_optimize_frames_debug(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams,
+                              const double* lr_xyz_host,
+                              float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
+                              const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
+                              float* final_loss, void* workspace, int dbg_frame, int dbg_step, int* dbg_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-frame setup on the GPU.

@@ -22,13 +22,28 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def dependencies():
+    return sorted(sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+
+
+def source_hash():
+    """sha256 over every kernel source / header, in name order: compiled into the library (ssb_source_hash) and compared by
+    lib.lib() on load, so a git-ignored .so built from older sources is refused instead of running silently."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in dependencies():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + \
-        glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in dependencies())
 
 
 def build(force=False, verbose=False, defines=(), out=None):
@@ -37,7 +52,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     out = OUT if out is None else out
-    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
+    cmd = [NVCC] + FLAGS + [f'-DSSB_SOURCE_HASH="{source_hash()}"'] + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

@@ -11,7 +11,11 @@ int ssb_set_cuda_error(cudaError_t e) {
 }
 
 extern "C" {
-int ssb_version(void) { return 101; }
+int ssb_version(void) { return 200; }
+#ifndef SSB_SOURCE_HASH
+#define SSB_SOURCE_HASH "unknown"
+#endif
+const char* ssb_source_hash(void) { return SSB_SOURCE_HASH; }
 // sizeof of the ABI structs (0: ssb_gaussians, 1: ssb_cameras, 2: ssb_opt_config): lets a binding verify its struct layout
 int ssb_struct_size(int which) {
     switch (which) {

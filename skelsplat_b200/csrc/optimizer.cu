@@ -78,6 +78,8 @@ struct OptParams {
     float* xyz; float* scaling_raw; float* rotation_raw; float* opacity_raw;
     const int* roi_rect; const int64_t* roi_offset; const float* roi_data;
     float* final_loss; int* status;
+    // debug accessor (ssb_optimize_frames_debug; NULL in production): the binning of frame dbg_frame at Adam step dbg_step
+    int* dbg; int dbg_frame, dbg_step;
 };
 
 // Reduce V (power of two) values across the warp with V-1+log2(32/V) shuffles.  On return every lane
@@ -423,11 +425,16 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
 }
 
 // NT threads per CTA: 512 with two CTAs per SM, or 1024 with one when the binning state (r_capacity) is too large for two.
-template <int SLOTS, int NT>
+// HALVES: the per-(tile,Gaussian) records (32 of the 40 B/pair of binning state) are held for SLOTS/HALVES slots at a time: with
+// HALVES == 2 the tile phase runs twice per Adam step (slots 0-1, then 2-3) over the same record storage, which keeps two CTAs
+// per SM up to r_capacity 1024 (Panoptic).  Same records, same fixed-order sums => bit-identical results.
+template <int SLOTS, int NT, int HALVES>
 __global__ void __launch_bounds__(NT, (NT >= 1024 ? 1 : SSB_OPT_MIN_CTAS))
 optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ StepTable tab)
 {
     constexpr int NW = NT / 32;
+    constexpr int RSLOTS = SLOTS / HALVES;     // slots whose records are resident at once
+    static_assert(SLOTS % HALVES == 0, "HALVES must divide SLOTS");
     const int J = p.cfg.J, V = p.cfg.V, RCAP = p.cfg.r_capacity;
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -453,14 +460,14 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ float s_lsum[SLOTS][NW];
     __shared__ int s_status;
     extern __shared__ __align__(16) unsigned char dsm[];
-    // dynamic, per slot: partial f32[RCAP*PSTRIDE] (32 B/entry) whose storage is first used by the sort's 32-bit words
-    // (dead once the tile lists exist) | list u16 | inv_pos u16 | tile u16 | start u16  => 40 B/entry
+    // dynamic: partial f32[RSLOTS][RCAP*PSTRIDE] (32 B/entry) whose storage is first used by the sort's 32-bit words of all
+    // SLOTS slots (dead once the tile lists exist) | per slot: list u16 | inv_pos u16 | tile u16 | start u16  (8 B/entry)
     float* d_part = reinterpret_cast<float*>(dsm);
-    uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)SLOTS * RCAP * PSTRIDE);
+    uint16_t* d_list = reinterpret_cast<uint16_t*>(d_part + (size_t)RSLOTS * RCAP * PSTRIDE);
     uint16_t* d_inv = d_list + (size_t)SLOTS * RCAP;
     uint16_t* d_tile = d_inv + (size_t)SLOTS * RCAP;
     uint16_t* d_start = d_tile + (size_t)SLOTS * RCAP;
-#define SSB_KEYS32(k) (reinterpret_cast<uint32_t*>(d_part + (size_t)(k) * RCAP * PSTRIDE))
+#define SSB_KEYS32(k) (reinterpret_cast<uint32_t*>(d_part) + (size_t)(k) * RCAP)
 
     // ---------------- load the frame ----------------
     for (int i = tid; i < J * 3; i += NT) { s_xyz[i] = p.xyz[(size_t)frame * J * 3 + i]; s_scal[i] = p.scaling_raw[(size_t)frame * J * 3 + i]; }
@@ -633,17 +640,35 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             if (lane == 0) s_nact[k] = nact;
         }
         __syncthreads();
+        if (p.dbg && frame == p.dbg_frame && step == p.dbg_step) {
+            // per slot k, 4 + 4 RCAP int32: (R, active tiles, view, status) | list[RCAP] | inv_pos[RCAP] | tile[RCAP] | start[RCAP]
+            for (int i = tid; i < SLOTS * RCAP; i += NT) {
+                const int k = i / RCAP, e = i - k * RCAP;
+                int* o = p.dbg + (size_t)k * (4 + 4 * RCAP) + 4;
+                o[e] = e < s_R[k] ? (int)d_list[i] : -1;
+                o[RCAP + e] = e < s_R[k] ? (int)d_inv[i] : -1;
+                o[2 * RCAP + e] = e < s_nact[k] ? (int)d_tile[i] : -1;
+                o[3 * RCAP + e] = e < s_nact[k] ? (int)d_start[i] : -1;
+            }
+            if (tid < SLOTS) {
+                int* o = p.dbg + (size_t)tid * (4 + 4 * RCAP);
+                o[0] = s_R[tid]; o[1] = s_nact[tid]; o[2] = s_slot_view[tid]; o[3] = s_status;
+            }
+        }
 
         SSB_PHASE_MARK(3)
         // ============ phase C: tiles.  One warp per active tile, handed out dynamically (tile lists differ in length);
         // every result is a per-(tile,Gaussian) record, so the schedule does not influence any sum ============
+        float s8[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int half = 0; half < HALVES; half++) {
         {
             const float* roi_base = p.roi_data + s_roi_base;
             const bool unroll5 = p.cfg.max_unrolled_list != 4;          // 0 (default) or 5: lists of five take tile_fast<5>
             // one counter per slot; a warp starts on slot (warp mod SLOTS) and moves on when that slot's tiles are handed out,
             // so everything that depends on the slot only (view, image size, splat table) is loaded once per slot, not per tile
-            for (int kk = 0; kk < SLOTS; kk++) {
-            const int k = (warp + kk) & (SLOTS - 1);
+            for (int kk = 0; kk < RSLOTS; kk++) {
+            const int k = half * RSLOTS + ((warp + kk) & (RSLOTS - 1));
             const int nact = s_nact[k];
             const int v = s_slot_view[k];
             const int W = s_W[v], H = s_H[v];
@@ -662,7 +687,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                 if (lane == 0) atomicAdd(&g_list_hist[n < 23 ? n : 23], 1ull);
 #endif
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
-                float* part_out = d_part + ((size_t)k * RCAP + e0) * PSTRIDE;
+                float* part_out = d_part + ((size_t)(k - half * RSLOTS) * RCAP + e0) * PSTRIDE;
 #define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
                 if (n == 1) { const int g1 = list[0]; tile_one<SSB_PP_N1>(sp, g1, s_roi[v][g1], s_roi_rel[v][g1], roi_base, lx, ly0, W, H, part_out, lane); }
                 else if (n == 2) tile_two(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
@@ -741,14 +766,13 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         SSB_PHASE_MARK(4)
         // ============ phase D: per-Gaussian backward chain + gradient bookkeeping ============
         // D1: fixed-order (emission order) sum of each Gaussian's per-tile records
-        float s8[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (tid < SLOTS * J) {
+        if (tid < SLOTS * J && tid / J / RSLOTS == half) {
             const int k = tid / J, j = tid % J;
             const SlotSplats& sp = s_sp[k];
             if (sp.tiles[j] > 0) {
                 const int o0 = (j == 0) ? 0 : sp.offs[j - 1], o1 = min((int)sp.offs[j], s_R[k]);
                 for (int o = o0; o < o1; o++) {
-                    const float* pp = d_part + ((size_t)k * RCAP + d_inv[(size_t)k * RCAP + o]) * PSTRIDE;
+                    const float* pp = d_part + ((size_t)(k - half * RSLOTS) * RCAP + d_inv[(size_t)k * RCAP + o]) * PSTRIDE;
 #pragma unroll
                     for (int q = 0; q < PSTRIDE; q++) s8[q] += pp[q];
                 }
@@ -757,6 +781,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             s_jcnt[k][j] = s8[7];
         }
         __syncthreads();
+        }   // half
         // D2: mask size N of the slot's view, then the chain
         if (tid < SLOTS * J) {
             const int k = tid / J, j = tid % J;
@@ -866,8 +891,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     (void)last_loss;
 }
 
-static size_t opt_dyn_smem(int slots, int rcap) {
-    return (size_t)slots * rcap * (4 * PSTRIDE + 2 * 4);
+static size_t opt_dyn_smem(int slots, int rcap, int halves) {
+    return (size_t)(slots / halves) * rcap * (4 * PSTRIDE) + (size_t)slots * rcap * (2 * 4);
 }
 
 }  // namespace ssb
@@ -893,13 +918,16 @@ size_t ssb_optimize_workspace_bytes(const ssb_opt_config* cfg, int n_frames) {
     return (size_t)(n_frames > 0 ? n_frames : 1) * sizeof(int);     // per-frame status words
 }
 
-int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams, const double* lr_xyz_host,
-                        float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
-                        const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
-                        float* final_loss, void* workspace, void* stream_)
+static int optimize_frames_impl(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams, const double* lr_xyz_host,
+                                float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
+                                const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
+                                float* final_loss, void* workspace, int dbg_frame, int dbg_step, int* dbg_out, void* stream_)
 {
     if (!cfg || !cams || !lr_xyz_host || n_frames < 0) return SSB_ERR_INVALID;
     if (cfg->J <= 0 || cfg->J > MAXJ || cfg->V <= 0 || cfg->V > MAXV || cams->n_views != cfg->V) return SSB_ERR_UNSUPPORTED;
+    // tile coordinates are packed as (y << 8) | x in 16 bits: at most 256 tiles (4096 px) per axis.  W0/H0 are the maxima
+    // over the views (ssb_cameras), so dims[] on the device may not exceed them.
+    if (cams->W0 <= 0 || cams->H0 <= 0 || cams->W0 > 4096 || cams->H0 > 4096) return SSB_ERR_UNSUPPORTED;
     if (cfg->accumulation_steps < 1 || cfg->accumulation_steps > MAX_SLOTS || cfg->accumulation_steps == 3) return SSB_ERR_UNSUPPORTED;
     if (cfg->r_capacity < 32 || cfg->r_capacity > 1024 || (cfg->r_capacity % 32)) return SSB_ERR_CAPACITY;
     if (cfg->max_unrolled_list != 0 && cfg->max_unrolled_list != 4 && cfg->max_unrolled_list != 5) return SSB_ERR_INVALID;
@@ -928,30 +956,57 @@ int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_camer
     p.xyz = xyz; p.scaling_raw = scaling_raw; p.rotation_raw = rotation_raw; p.opacity_raw = opacity_raw;
     p.roi_rect = roi_rect; p.roi_offset = roi_offset; p.roi_data = roi_data; p.final_loss = final_loss;
     p.status = (int*)workspace;
+    p.dbg = dbg_out; p.dbg_frame = dbg_frame; p.dbg_step = dbg_step;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int slots = cfg->accumulation_steps;
-    const size_t smem = opt_dyn_smem(slots, cfg->r_capacity);
-    // two 512-thread CTAs per SM when their shared memory fits (227 KB/SM), else one 1024-thread CTA: 32 warps/SM either way
-    const bool big = (SSB_OPT_MIN_CTAS * (smem + 17 * 1024) > 227 * 1024);
+    // Launch shape.  Two 512-thread CTAs per SM whenever their shared memory fits (227 KB/SM; static + 1 KB reserved per CTA
+    // = 17 KB): with all slots' records resident if possible, else (4 slots only) with the records of two slots at a time;
+    // beyond that one 1024-thread CTA per SM.  32 warps/SM either way.
+    auto fits2 = [&](int halves) { return SSB_OPT_MIN_CTAS * (opt_dyn_smem(slots, cfg->r_capacity, halves) + 17 * 1024) <= 227 * 1024; };
+    if (cfg->resident_record_slots != 0 && cfg->resident_record_slots != slots && !(slots == 4 && cfg->resident_record_slots == 2)) return SSB_ERR_INVALID;
+    const int halves = cfg->resident_record_slots ? slots / cfg->resident_record_slots : (fits2(1) ? 1 : ((slots == 4 && fits2(2)) ? 2 : 1));
+    const bool big = !fits2(halves);
+    const size_t smem = opt_dyn_smem(slots, cfg->r_capacity, halves);
+#define SSB_LAUNCH_OPT_K(S, NTH, HV)                                                                              \
+    {                                                                                                             \
+        if (cudaFuncSetAttribute(optimize_kernel<S, NTH, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+            return ssb_set_cuda_error(cudaGetLastError());                                                        \
+        optimize_kernel<S, NTH, HV><<<n_frames, NTH, smem, stream>>>(p, tab);                                     \
+    }
 #define SSB_LAUNCH_OPT(S)                                                                                         \
     {                                                                                                             \
-        if (big) {                                                                                                \
-            if (cudaFuncSetAttribute(optimize_kernel<S, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-                return ssb_set_cuda_error(cudaGetLastError());                                                    \
-            optimize_kernel<S, 1024><<<n_frames, 1024, smem, stream>>>(p, tab);                                   \
-        } else {                                                                                                  \
-            if (cudaFuncSetAttribute(optimize_kernel<S, OPT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
-                return ssb_set_cuda_error(cudaGetLastError());                                                    \
-            optimize_kernel<S, OPT_THREADS><<<n_frames, OPT_THREADS, smem, stream>>>(p, tab);                     \
-        }                                                                                                         \
+        if (big) SSB_LAUNCH_OPT_K(S, 1024, 1)                                                                     \
+        else SSB_LAUNCH_OPT_K(S, OPT_THREADS, 1)                                                                  \
     }
     switch (slots) {
         case 1: SSB_LAUNCH_OPT(1) break;
         case 2: SSB_LAUNCH_OPT(2) break;
-        case 4: SSB_LAUNCH_OPT(4) break;
+        case 4:
+            if (halves == 2) SSB_LAUNCH_OPT_K(4, OPT_THREADS, 2)
+            else SSB_LAUNCH_OPT(4)
+            break;
         default: return SSB_ERR_UNSUPPORTED;
     }
     return ssb_set_cuda_error(cudaGetLastError());
+}
+
+int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams, const double* lr_xyz_host,
+                        float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
+                        const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
+                        float* final_loss, void* workspace, void* stream_)
+{
+    return optimize_frames_impl(cfg, n_frames, cams, lr_xyz_host, xyz, scaling_raw, rotation_raw, opacity_raw, roi_rect, roi_offset,
+                                roi_data, final_loss, workspace, -1, -1, nullptr, stream_);
+}
+
+int ssb_optimize_frames_debug(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams, const double* lr_xyz_host,
+                              float* xyz, float* scaling_raw, float* rotation_raw, float* opacity_raw,
+                              const int* roi_rect, const int64_t* roi_offset, const float* roi_data,
+                              float* final_loss, void* workspace, int dbg_frame, int dbg_step, int* dbg_out, void* stream_)
+{
+    if (!dbg_out || dbg_frame < 0 || dbg_frame >= n_frames || dbg_step < 0) return SSB_ERR_INVALID;
+    return optimize_frames_impl(cfg, n_frames, cams, lr_xyz_host, xyz, scaling_raw, rotation_raw, opacity_raw, roi_rect, roi_offset,
+                                roi_data, final_loss, workspace, dbg_frame, dbg_step, dbg_out, stream_);
 }
 
 }  // extern "C"

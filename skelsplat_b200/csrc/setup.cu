@@ -76,7 +76,9 @@ __global__ void dlt_kernel(int F, int V, int J, const double* __restrict__ P, co
 }
 
 // ------------------------------------------------------------------------------------------ heatmap ROIs
-// sigma of the (view, joint) heatmap from the INITIAL Gaussian, restating utils/general_utils.py:199-265 in fp32:
+// sigma of the (view, joint) heatmap from the INITIAL Gaussian, restating utils/general_utils.py:199-265 (fp32 torch ops on
+// the reference's GPU) in fp64 with a fixed operation order, rounded to fp32 at the end -- the form in which the host
+// specification and this kernel agree exactly on every integer window:
 // T = R_w2c @ J_rows (not the rasteriser's EWA form), cov = T^T Sigma^T T, +0.3 on the diagonal,
 // lambda = mid +- sqrt(max(0.1, mid^2 - det)); sigma_y = sqrt(lambda1) (axis 0), sigma_x = sqrt(lambda2) (axis 1).
 struct RoiParams {
@@ -87,7 +89,14 @@ struct RoiParams {
     float scaling_modifier;
 };
 
-__device__ __forceinline__ int gauss_radius(float sigma) { return (int)(4.0f * sigma + 0.5f); }   // scipy: int(truncate*sd + 0.5)
+__device__ __forceinline__ int gauss_radius(float sigma) { return (int)(4.0 * (double)sigma + 0.5); }   // scipy: int(truncate * sd + 0.5), python floats
+
+// fp64 without FMA contraction: the host specification (skelsplat_b200/heatmaps.py:heatmap_sigmas) performs the same IEEE
+// operations in the same order in numpy float64, so both sides produce the same sigma (and hence the same integer window).
+__device__ __forceinline__ double dm(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double ds(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dd(double a, double b) { return __ddiv_rn(a, b); }
 
 __global__ void roi_rect_kernel(RoiParams p, int* __restrict__ roi_rect, float* __restrict__ roi_sigma, int* __restrict__ roi_center,
                                 long long* __restrict__ roi_size)
@@ -96,48 +105,48 @@ __global__ void roi_rect_kernel(RoiParams p, int* __restrict__ roi_rect, float* 
     if (i >= p.F * p.V * p.J) return;
     const int j = i % p.J, v = (i / p.J) % p.V, f = i / (p.J * p.V);
     const int W = p.cams.dims ? p.cams.dims[2 * v] : p.cams.W0, H = p.cams.dims ? p.cams.dims[2 * v + 1] : p.cams.H0;
-    const float tfx = p.cams.tanfov ? p.cams.tanfov[2 * v] : p.cams.tanfovx0, tfy = p.cams.tanfov ? p.cams.tanfov[2 * v + 1] : p.cams.tanfovy0;
-    const float* vm = p.cams.viewmatrix + 16 * v;            // stored transposed: W2C(r,c) = vm[4*c + r]
+    const double tfx = (double)(p.cams.tanfov ? p.cams.tanfov[2 * v] : p.cams.tanfovx0), tfy = (double)(p.cams.tanfov ? p.cams.tanfov[2 * v + 1] : p.cams.tanfovy0);
+    double vm[16];                                           // stored transposed: W2C(r,c) = vm[4*c + r]
+    for (int k = 0; k < 16; k++) vm[k] = (double)p.cams.viewmatrix[16 * v + k];
     const size_t gj = (size_t)f * p.J + j;
-    const float mx = p.xyz[3 * gj], my = p.xyz[3 * gj + 1], mz = p.xyz[3 * gj + 2];
+    const double mx = (double)p.xyz[3 * gj], my = (double)p.xyz[3 * gj + 1], mz = (double)p.xyz[3 * gj + 2];
     // Sigma = (R S)(R S)^T with the NORMALISED quaternion (build_rotation normalises, general_utils.py:87-108)
-    float q0 = p.rotation_raw[4 * gj], q1 = p.rotation_raw[4 * gj + 1], q2 = p.rotation_raw[4 * gj + 2], q3 = p.rotation_raw[4 * gj + 3];
-    const float qn = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-    q0 /= qn; q1 /= qn; q2 /= qn; q3 /= qn;
-    const float r = q0, x = q1, y = q2, z = q3;
-    const float R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y)},
-                           {2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x)},
-                           {2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)}};
-    float s[3];
-    for (int k = 0; k < 3; k++) s[k] = expf(p.scaling_raw[3 * gj + k]) * p.scaling_modifier;
-    float Sg[3][3];
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
-        float acc = 0.f;
-        for (int k = 0; k < 3; k++) acc += (R[a][k] * s[k]) * (R[b][k] * s[k]);
-        Sg[a][b] = acc;
+    const double q0 = (double)p.rotation_raw[4 * gj], q1 = (double)p.rotation_raw[4 * gj + 1], q2 = (double)p.rotation_raw[4 * gj + 2], q3 = (double)p.rotation_raw[4 * gj + 3];
+    const double qn = __dsqrt_rn(da(da(da(dm(q0, q0), dm(q1, q1)), dm(q2, q2)), dm(q3, q3)));
+    const double r = dd(q0, qn), x = dd(q1, qn), y = dd(q2, qn), z = dd(q3, qn);
+    const double R[3][3] = {{ds(1.0, dm(2.0, da(dm(y, y), dm(z, z)))), dm(2.0, ds(dm(x, y), dm(r, z))), dm(2.0, da(dm(x, z), dm(r, y)))},
+                            {dm(2.0, da(dm(x, y), dm(r, z))), ds(1.0, dm(2.0, da(dm(x, x), dm(z, z)))), dm(2.0, ds(dm(y, z), dm(r, x)))},
+                            {dm(2.0, ds(dm(x, z), dm(r, y))), dm(2.0, da(dm(y, z), dm(r, x))), ds(1.0, dm(2.0, da(dm(x, x), dm(y, y))))}};
+    double M[3][3];
+    for (int k = 0; k < 3; k++) {
+        const double sk = dm(exp((double)p.scaling_raw[3 * gj + k]), (double)p.scaling_modifier);
+        for (int a = 0; a < 3; a++) M[a][k] = dm(R[a][k], sk);
     }
-    float t[3];
-    for (int a = 0; a < 3; a++) t[a] = vm[a] * mx + vm[4 + a] * my + vm[8 + a] * mz + vm[12 + a];
-    const float fx = (float)W / (2.0f * tfx), fy = (float)H / (2.0f * tfy);
-    const float limx = 1.3f * tfx, limy = 1.3f * tfy;
-    t[0] = fminf(limx, fmaxf(-limx, t[0] / t[2])) * t[2];
-    t[1] = fminf(limy, fmaxf(-limy, t[1] / t[2])) * t[2];
-    const float Jr[2][3] = {{fx / t[2], 0.f, -(fx * t[0]) / (t[2] * t[2])}, {0.f, fy / t[2], -(fy * t[1]) / (t[2] * t[2])}};
+    double Sg[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Sg[a][b] = da(da(dm(M[a][0], M[b][0]), dm(M[a][1], M[b][1])), dm(M[a][2], M[b][2]));
+    double t[3];
+    for (int a = 0; a < 3; a++) t[a] = da(da(da(dm(vm[a], mx), dm(vm[4 + a], my)), dm(vm[8 + a], mz)), vm[12 + a]);
+    const double fx = dd((double)W, dm(2.0, tfx)), fy = dd((double)H, dm(2.0, tfy));
+    const double limx = dm(1.3, tfx), limy = dm(1.3, tfy);
+    t[0] = dm(fmin(limx, fmax(-limx, dd(t[0], t[2]))), t[2]);
+    t[1] = dm(fmin(limy, fmax(-limy, dd(t[1], t[2]))), t[2]);
+    const double tz2 = dm(t[2], t[2]);
+    const double Jr[2][3] = {{dd(fx, t[2]), 0.0, -dd(dm(fx, t[0]), tz2)}, {0.0, dd(fy, t[2]), -dd(dm(fy, t[1]), tz2)}};
     // T = Wm @ Jm with Wm = W2C[:3,:3] and Jm rows (Jr[0], Jr[1], 0): T[a][b] = Wm[a][0]*Jr[0][b] + Wm[a][1]*Jr[1][b]
-    float T[3][3];
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) T[a][b] = vm[4 * 0 + a] * Jr[0][b] + vm[4 * 1 + a] * Jr[1][b];
+    double T[3][3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) T[a][b] = da(dm(vm[4 * 0 + a], Jr[0][b]), dm(vm[4 * 1 + a], Jr[1][b]));
     // cov = T^T Sigma^T T, entries (0,0), (0,1), (1,1)
-    float c00 = 0.f, c01 = 0.f, c11 = 0.f;
+    double c00 = 0.0, c01 = 0.0, c11 = 0.0;
     for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
-        c00 += T[a][0] * Sg[b][a] * T[b][0];
-        c01 += T[a][0] * Sg[b][a] * T[b][1];
-        c11 += T[a][1] * Sg[b][a] * T[b][1];
+        c00 = da(c00, dm(dm(T[a][0], Sg[b][a]), T[b][0]));
+        c01 = da(c01, dm(dm(T[a][0], Sg[b][a]), T[b][1]));
+        c11 = da(c11, dm(dm(T[a][1], Sg[b][a]), T[b][1]));
     }
-    const float cx = c00 + 0.3f, cz = c11 + 0.3f;
-    const float det = cx * cz - c01 * c01;
-    const float mid = 0.5f * (cx + cz);
-    const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
-    const float s1 = sqrtf(mid + root), s2 = sqrtf(mid - root);
+    const double cx = da(c00, 0.3), cz = da(c11, 0.3);
+    const double det = ds(dm(cx, cz), dm(c01, c01));
+    const double mid = dm(0.5, da(cx, cz));
+    const double root = __dsqrt_rn(fmax(0.1, ds(dm(mid, mid), det)));
+    const float s1 = (float)__dsqrt_rn(da(mid, root)), s2 = (float)__dsqrt_rn(ds(mid, root));   // fp32 like the tensor .item() reads
     // peak at (clamp(int(v)), clamp(int(u))): .long() truncates toward zero (general_utils.py:275-278)
     const float u = p.poses_2d[2 * (size_t)i], vv = p.poses_2d[2 * (size_t)i + 1];
     const int xc = min(max((int)u, 0), W - 1), yc = min(max((int)vv, 0), H - 1);

@@ -45,34 +45,54 @@ def covariance_3d(scaling_raw, rotation, scaling_modifier=1.0):
     return (L @ L.transpose(0, 2, 1)).astype(np.float32)
 
 
-def heatmap_sigmas(xyz, cams, cov3d):
-    """(sigma_y, sigma_x), each [V,J] float32 -- general_utils.py:199-265 in numpy float32."""
-    f32 = np.float32
+def heatmap_sigmas(xyz, cams, scaling_raw, rotation, scaling_modifier=1.0):
+    """(sigma_y, sigma_x), each [V,J] float32 -- general_utils.py:199-265.
+
+    The reference evaluates this with fp32 torch ops on its GPU; the window half-width ``int(4*sigma + 0.5)`` is a step
+    function of sigma, so two fp32 evaluations that differ in the last bit disagree on ~3 % of the windows.  The
+    specification is therefore written in float64 with a FIXED operation order (plain IEEE add/mul/div/sqrt on numpy
+    float64 arrays: no matmul, no FMA) and rounded to fp32 at the end, which is what ``.item()`` of the reference's fp32
+    tensor hands to the filter; csrc/setup.cu:roi_rect_kernel performs the same operations in the same order, so host and
+    GPU agree on every window (tests/test_gpu_setup.py asserts 100 %)."""
+    f64 = np.float64
     V, J = len(cams), xyz.shape[0]
-    xyz = xyz.astype(f32)
-    s1 = np.zeros((V, J), f32); s2 = np.zeros((V, J), f32)
-    hom = np.concatenate([xyz, np.ones((J, 1), f32)], 1)
+    m = xyz.astype(np.float32).astype(f64)
+    q = rotation.astype(np.float32).astype(f64)
+    sr = scaling_raw.astype(np.float32).astype(f64)
+    mod = f64(np.float32(scaling_modifier))
+    qn = np.sqrt(((q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1]) + q[:, 2] * q[:, 2]) + q[:, 3] * q[:, 3])
+    r, x, y, z = q[:, 0] / qn, q[:, 1] / qn, q[:, 2] / qn, q[:, 3] / qn
+    R = [[1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - r * z), 2.0 * (x * z + r * y)],
+         [2.0 * (x * y + r * z), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - r * x)],
+         [2.0 * (x * z - r * y), 2.0 * (y * z + r * x), 1.0 - 2.0 * (x * x + y * y)]]
+    sk = [np.exp(sr[:, k]) * mod for k in range(3)]
+    M = [[R[a][k] * sk[k] for k in range(3)] for a in range(3)]
+    Sg = [[(M[a][0] * M[b][0] + M[a][1] * M[b][1]) + M[a][2] * M[b][2] for b in range(3)] for a in range(3)]
+    s1 = np.zeros((V, J), np.float32); s2 = np.zeros((V, J), np.float32)
     for v, cam in enumerate(cams):
-        view = cam.world_view_transform.T.astype(f32)          # = W2C
-        tanx, tany = f32(np.tan(f32(cam.FoVx * 0.5))), f32(np.tan(f32(cam.FoVy * 0.5)))
-        fx = f32(cam.image_width) / (f32(2.0) * tanx)
-        fy = f32(cam.image_height) / (f32(2.0) * tany)
-        t = (view @ hom.T).T[:, :3].astype(f32)
-        limx, limy = f32(1.3) * tanx, f32(1.3) * tany
-        txtz, tytz = t[:, 0] / t[:, 2], t[:, 1] / t[:, 2]
-        t[:, 0] = np.clip(txtz, -limx, limx) * t[:, 2]
-        t[:, 1] = np.clip(tytz, -limy, limy) * t[:, 2]
-        Jm = np.zeros((J, 3, 3), f32)
-        Jm[:, 0, 0] = fx / t[:, 2]; Jm[:, 0, 2] = -(fx * t[:, 0]) / t[:, 2] ** 2
-        Jm[:, 1, 1] = fy / t[:, 2]; Jm[:, 1, 2] = -(fy * t[:, 1]) / t[:, 2] ** 2
-        T = view[None, :3, :3] @ Jm
-        cov = T.transpose(0, 2, 1) @ cov3d.transpose(0, 2, 1) @ T
-        cx = cov[:, 0, 0] + f32(0.3); cy = cov[:, 0, 1]; cz = cov[:, 1, 1] + f32(0.3)
-        det = cx * cz - cy * cy
-        mid = f32(0.5) * (cx + cz)
-        root = np.sqrt(np.maximum(f32(0.1), mid * mid - det))
-        s1[v] = np.sqrt(mid + root)
-        s2[v] = np.sqrt(mid - root)
+        vm = cam.world_view_transform.astype(np.float32).reshape(16).astype(f64)     # W2C(r, c) = vm[4 c + r]
+        tfx, tfy = f64(np.float32(cam.tanfovx)), f64(np.float32(cam.tanfovy))
+        t = [((vm[a] * m[:, 0] + vm[4 + a] * m[:, 1]) + vm[8 + a] * m[:, 2]) + vm[12 + a] for a in range(3)]
+        fx, fy = f64(cam.image_width) / (2.0 * tfx), f64(cam.image_height) / (2.0 * tfy)
+        limx, limy = 1.3 * tfx, 1.3 * tfy
+        t[0] = np.minimum(limx, np.maximum(-limx, t[0] / t[2])) * t[2]
+        t[1] = np.minimum(limy, np.maximum(-limy, t[1] / t[2])) * t[2]
+        tz2 = t[2] * t[2]
+        zero = np.zeros(J, f64)
+        Jr = [[fx / t[2], zero, -((fx * t[0]) / tz2)], [zero, fy / t[2], -((fy * t[1]) / tz2)]]
+        T = [[vm[a] * Jr[0][b] + vm[4 + a] * Jr[1][b] for b in range(3)] for a in range(3)]
+        c00 = np.zeros(J, f64); c01 = np.zeros(J, f64); c11 = np.zeros(J, f64)
+        for a in range(3):
+            for b in range(3):
+                c00 = c00 + (T[a][0] * Sg[b][a]) * T[b][0]
+                c01 = c01 + (T[a][0] * Sg[b][a]) * T[b][1]
+                c11 = c11 + (T[a][1] * Sg[b][a]) * T[b][1]
+        cx, cz = c00 + 0.3, c11 + 0.3
+        det = cx * cz - c01 * c01
+        mid = 0.5 * (cx + cz)
+        root = np.sqrt(np.maximum(0.1, mid * mid - det))
+        s1[v] = np.sqrt(mid + root).astype(np.float32)
+        s2[v] = np.sqrt(mid - root).astype(np.float32)
     return s1, s2
 
 
@@ -115,12 +135,29 @@ class HeatmapROIs:
         return self.data[o:o + w * h].reshape(h, w)
 
 
+def heatmap_roi_rects(xyz_init, poses_2d, cams, scaling_raw, rotation, scaling_modifier=1.0):
+    """Only the integer windows (x0, y0, w, h) [V,J,4] of generate_heatmap_rois -- the part that must agree EXACTLY between
+    this specification and csrc/setup.cu:roi_rect_kernel (cheap enough to check on thousands of frames)."""
+    V, J = len(cams), xyz_init.shape[0]
+    poses_2d = np.asarray(poses_2d, np.float32)                    # the detections are an fp32 tensor when .long() truncates them
+    s1, s2 = heatmap_sigmas(xyz_init, cams, scaling_raw, rotation, scaling_modifier)
+    rect = np.zeros((V, J, 4), np.int32)
+    for v, cam in enumerate(cams):
+        W, H = cam.image_width, cam.image_height
+        for j in range(J):
+            xc = int(np.clip(int(poses_2d[v, j, 0]), 0, W - 1)); yc = int(np.clip(int(poses_2d[v, j, 1]), 0, H - 1))
+            ry, rx = int(4.0 * float(s1[v, j]) + 0.5), int(4.0 * float(s2[v, j]) + 0.5)
+            x0, x1, y0, y1 = max(0, xc - rx), min(W - 1, xc + rx), max(0, yc - ry), min(H - 1, yc + ry)
+            rect[v, j] = (x0, y0, x1 - x0 + 1, y1 - y0 + 1)
+    return rect
+
+
 def generate_heatmap_rois(xyz_init, poses_2d, cams, scaling_raw, rotation, scaling_modifier=1.0):
     """ROI form of generate_heatmaps (utils/general_utils.py:175-297)."""
     f32 = np.float32
     V, J = len(cams), xyz_init.shape[0]
-    cov3d = covariance_3d(scaling_raw, rotation, scaling_modifier)
-    s1, s2 = heatmap_sigmas(xyz_init, cams, cov3d)
+    poses_2d = np.asarray(poses_2d, np.float32)                    # the detections are an fp32 tensor when .long() truncates them
+    s1, s2 = heatmap_sigmas(xyz_init, cams, scaling_raw, rotation, scaling_modifier)
     rect = np.zeros((V, J, 4), np.int32); offset = np.zeros((V, J), np.int64)
     chunks, total = [], 0
     for v, cam in enumerate(cams):

@@ -39,18 +39,19 @@ class OptConfig(C.Structure):
                 ("lambda_consistency", C.c_float), ("limb_pairs", C.c_int * 8),
                 ("lr_scaling", C.c_float), ("lr_rotation", C.c_float), ("lr_opacity", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("r_capacity", C.c_int), ("antialiasing", C.c_int), ("max_unrolled_list", C.c_int)]
+                ("r_capacity", C.c_int), ("antialiasing", C.c_int), ("max_unrolled_list", C.c_int),
+                ("resident_record_slots", C.c_int)]
 
 
 _lib = None
 
 EXPORTS = [
-    "ssb_version", "ssb_struct_size", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
+    "ssb_version", "ssb_source_hash", "ssb_struct_size", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
     "ssb_state_bytes", "ssb_rasterize_forward", "ssb_backward_scratch_bytes", "ssb_rasterize_backward",
     "ssb_mark_visible", "ssb_state_field_offset",
     "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency",
     "ssb_fused_ssim_forward", "ssb_fused_ssim_backward",
-    "ssb_optimize_workspace_bytes", "ssb_optimize_frames",
+    "ssb_optimize_workspace_bytes", "ssb_optimize_frames", "ssb_optimize_frames_debug",
     "ssb_triangulate_dlt", "ssb_heatmap_roi_rects", "ssb_heatmap_roi_offsets", "ssb_heatmap_roi_fill",
 ]
 
@@ -72,6 +73,14 @@ def lib():
         if missing:
             raise SkelSplatLibraryError(f"{LIB_PATH} is stale, missing symbols {missing}: rebuild it")
         L.ssb_error_string.restype = C.c_char_p
+        L.ssb_source_hash.restype = C.c_char_p
+        if "SKELSPLAT_B200_LIB" not in os.environ:                  # tuning variants are built with other defines on purpose
+            from . import build as _b
+            if os.path.isdir(_b.CSRC) and _b.sources():
+                built, now = L.ssb_source_hash().decode(), _b.source_hash()
+                if built != now:
+                    raise SkelSplatLibraryError(f"{LIB_PATH} is stale: built from sources {built}, the tree holds {now}: rebuild it "
+                                                "(python -m skelsplat_b200.build)")
         L.ssb_last_cuda_error.restype = C.c_char_p
         L.ssb_state_bytes.restype = C.c_size_t
         L.ssb_backward_scratch_bytes.restype = C.c_size_t

@@ -129,9 +129,13 @@ def project(cam: ViewCamera, X):
     return uv[:, :2] / uv[:, 2:3]
 
 
-def make_sequence(cfg: SceneConfig, n_frames: int, seed: int = 0) -> Sequence:
+def make_sequence(cfg: SceneConfig, n_frames: int, seed: int = 0, shard: int = None) -> Sequence:
+    """``shard`` (optional): the camera rig is that of ``seed`` but the frames come from an independent stream keyed by
+    (seed, shard) -- the shards of ONE sequence (one rig) that the ranks of a multi-GPU run optimise."""
     rng = np.random.default_rng(seed)
     cams = make_cameras(rng, cfg)
+    if shard is not None:
+        rng = np.random.default_rng([seed, 7919 + shard])
     frames = []
     P_list = [c.P3x4() for c in cams]
     for f in range(n_frames):

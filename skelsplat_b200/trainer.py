@@ -138,6 +138,7 @@ def make_opt_config(cfg: SceneConfig, r_capacity=256, iterations=None):
     oc.r_capacity = r_capacity
     oc.antialiasing = int(cfg.antialiasing)
     oc.max_unrolled_list = int(os.environ.get("SKELSPLAT_B200_UNROLL", tuned_max_unrolled_list(cfg)))
+    oc.resident_record_slots = int(os.environ.get("SKELSPLAT_B200_RECORD_SLOTS", 0))      # 0 = auto (developer knob; results are bit-identical)
     return oc
 
 
@@ -173,6 +174,44 @@ def _launch(ps: PackedSequence, oc, lr, final_loss):
                                _L.ptr(ps.roi_data), _L.ptr(final_loss), _L.ptr(ws), _L.current_stream())
     _L.check(rc, "ssb_optimize_frames")
     return ws[:F]
+
+
+def debug_binning(ps: PackedSequence, frame=0, step=0, r_capacity=None, iterations=None):
+    """Debug accessor (ssb_optimize_frames_debug): run the fused optimiser on a COPY of ``ps`` for ``iterations`` (default:
+    just far enough to reach Adam step ``step``) and return the kernel's own binning state of ``frame`` at that step, one dict
+    per slot (= iteration of the step group): view, R, point_list [R] (sorted Gaussian ids), inv_pos [R], tile_ids [n_active]
+    (row-major tile index y * grid_x + x), tile_starts [n_active].  This is what the parity tests compare bit-for-bit with
+    the dense op's / the reference's binningState (rasterizer_impl.cu:70-138, 303-320)."""
+    L = _L.lib()
+    cfg = ps.cfg
+    rcap = default_r_capacity(cfg) if r_capacity is None else r_capacity
+    acc = cfg.accumulation_steps
+    iters = (step + 1) * acc if iterations is None else iterations
+    oc = make_opt_config(cfg, rcap, iters)
+    lr = xyz_lr_table(cfg, ps.spatial_lr_scale, oc.iterations)
+    lr_c = (C.c_double * len(lr))(*lr.tolist())
+    cams = _L.Cameras(cfg.nviews, _L.ptr(ps.viewmatrix), _L.ptr(ps.projmatrix), _L.ptr(ps.dims), _L.ptr(ps.tanfov),
+                      ps.Wmax, ps.Hmax, 0.0, 0.0, int(cfg.antialiasing))
+    F = ps.xyz.shape[0]
+    st = [t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity)]
+    ws = torch.zeros(max(int(L.ssb_optimize_workspace_bytes(C.byref(oc), C.c_int(F))), 4) // 4, dtype=torch.int32, device=ps.xyz.device)
+    dbg = torch.full((acc, 4 + 4 * rcap), -1, dtype=torch.int32, device=ps.xyz.device)
+    rc = L.ssb_optimize_frames_debug(C.byref(oc), C.c_int(F), C.byref(cams), lr_c, _L.ptr(st[0]), _L.ptr(st[1]), _L.ptr(st[2]),
+                                     _L.ptr(st[3]), _L.ptr(ps.roi_rect), _L.ptr(ps.roi_offset), _L.ptr(ps.roi_data), None, _L.ptr(ws),
+                                     C.c_int(frame), C.c_int(step), _L.ptr(dbg), _L.current_stream())
+    _L.check(rc, "ssb_optimize_frames_debug")
+    d = dbg.cpu().numpy()
+    dims = ps.dims.cpu().numpy()
+    out = []
+    for k in range(acc):
+        R, nact, view, status = (int(x) for x in d[k, :4])
+        body = d[k, 4:].reshape(4, rcap)
+        gx = (int(dims[view, 0]) + 15) // 16
+        tile = body[2, :nact]
+        out.append(dict(view=view, R=R, n_active=nact, status=status, point_list=body[0, :R].astype(np.uint32),
+                        inv_pos=body[1, :R].astype(np.uint32), tile_ids=((tile >> 8) * gx + (tile & 255)).astype(np.uint32),
+                        tile_starts=body[3, :nact].astype(np.uint32)))
+    return out
 
 
 def optimize_packed(ps: PackedSequence, iterations=None, r_capacity=None, final_loss=None, check=True):

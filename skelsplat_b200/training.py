@@ -31,27 +31,41 @@ class TorchCamera:
         self.camera_center = torch.from_numpy(cam.camera_center).to(device)
 
 
-def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", iterations=None):
-    """One frame through the drop-in API; returns final xyz [J,3] float32 numpy."""
+def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", iterations=None, modules=None):
+    """One frame through the drop-in API; returns final xyz [J,3] float32 numpy.
+
+    ``modules``: optional (GaussianModel, render_functions, losses, consistency_losses) to run the same loop body on another
+    implementation of the same surface -- the tests pass the REFERENCE's own classes and functions here (tests/ref_import.py),
+    which is how "the reference's Python runs unchanged on the drop-in packages" is checked."""
     iterations = cfg.iterations if iterations is None else iterations
+    GM, rfuncs, loss_table, cons_table = modules if modules is not None else (GaussianModel, render_functions, losses, consistency_losses)
+    ref_surface = modules is not None
     opt = SimpleNamespace(position_lr_init=cfg.position_lr_init, position_lr_final=cfg.position_lr_final,
                           position_lr_delay_mult=cfg.position_lr_delay_mult, position_lr_max_steps=cfg.position_lr_max_steps,
                           feature_lr=cfg.feature_lr, opacity_lr=cfg.opacity_lr, scaling_lr=cfg.scaling_lr,
                           rotation_lr=cfg.rotation_lr, percent_dense=0.01)
     pipe = SimpleNamespace(debug=False, antialiasing=cfg.antialiasing, compute_cov3D_python=False, convert_SHs_python=False)
     data_root = "data/" + cfg.name
-    gaussians = GaussianModel(1, "default", device)
-    gaussians.create_from_pcd(np.asarray(frame.pose_3d_init, np.float32), cams, cameras_extent(cams), cfg.opacity_on, cfg.scaling,
-                              cfg.n_joints, cfg.scaling_modifier, cfg.name)
+    if ref_surface:      # the reference's signatures: GaussianModel(sh_degree, optimizer_type); create_from_pcd(pcd: BasicPointCloud, cam_infos, ...)
+        gaussians = GM(1, "default")
+        pts = np.asarray(frame.pose_3d_init, np.float32)
+        pcd = SimpleNamespace(points=pts, colors=np.zeros_like(pts), normals=np.zeros_like(pts))
+        cam_infos = [SimpleNamespace(image_name=f"cam{c.uid}") for c in cams]
+        opt.exposure_lr_init, opt.exposure_lr_final, opt.exposure_lr_delay_steps, opt.exposure_lr_delay_mult, opt.iterations = 0.01, 0.001, 0, 0.0, iterations
+        gaussians.create_from_pcd(pcd, cam_infos, cameras_extent(cams), cfg.opacity_on, cfg.scaling, cfg.n_joints, cfg.scaling_modifier, cfg.name)
+    else:
+        gaussians = GM(1, "default", device)
+        gaussians.create_from_pcd(np.asarray(frame.pose_3d_init, np.float32), cams, cameras_extent(cams), cfg.opacity_on, cfg.scaling,
+                                  cfg.n_joints, cfg.scaling_modifier, cfg.name)
     gaussians.training_setup(opt)
     tcams = [TorchCamera(c, device) for c in cams]
     if heatmaps_dense is None:
         rois = generate_heatmap_rois(np.asarray(frame.pose_3d_init), frame.poses_2d, cams,
                                      gaussians._scaling.detach().cpu().numpy(), gaussians._rotation.detach().cpu().numpy())
         heatmaps_dense = [torch.from_numpy(rois_to_dense(rois, v)).to(device) for v in range(len(cams))]
-    render = render_functions[cfg.rendering]
-    opt_criterion = losses[cfg.loss_function]
-    consistency_criterion = consistency_losses[cfg.consistency_loss]
+    render = rfuncs[cfg.rendering]
+    opt_criterion = loss_table[cfg.loss_function]
+    consistency_criterion = cons_table[cfg.consistency_loss]
     bg = torch.tensor([0, 0, 0], dtype=torch.float32, device=device)
     accumulated_grads = torch.zeros((len(tcams),) + tuple(gaussians.get_xyz.shape), device=device)
     poses_2d = torch.as_tensor(np.asarray(frame.poses_2d))

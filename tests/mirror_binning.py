@@ -1,4 +1,4 @@
-"""Host mirror (numpy, the readable specification) of the sort-free binning of the fused optimiser (optimizer.cu, phase B).
+"""TEST INFRASTRUCTURE (not imported by the product).  Host mirror (numpy, the readable specification) of the sort-free binning of the fused optimiser (optimizer.cu, phase B).
 
 The reference bins by sorting (tile << 32 | depth bits) keys with a stable radix sort (rasterizer_impl.cu:70-111, 303-320).
 Every Gaussian's tiles form a rectangle and there are at most 20 Gaussians, so the position of a (Gaussian j, tile t) pair in

@@ -1,4 +1,4 @@
-"""Host mirror (numpy, the readable specification) of what one view-iteration of the fused optimiser computes per tile
+"""TEST INFRASTRUCTURE (not imported by the product).  Host mirror (numpy, the readable specification) of what one view-iteration of the fused optimiser computes per tile
 (optimizer.cu, phase C + the first lines of phase D): forward replay, the one-hot scalar recurrence of the backward, the raw
 moment sums per Gaussian, the loss-mask size N and the mapping of the sums to dL/dmean2D, dL/dconic, dL/dopacity.
 

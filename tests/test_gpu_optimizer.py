@@ -192,3 +192,69 @@ def test_streaming_retries_only_the_overflowed_frames():
     out = so.result(so.submit({k: torch.from_numpy(v).pin_memory() for k, v in h.items()}))
     assert np.array_equal(out, ref)
     assert so.launches == 1
+
+
+def _dense_binning(cfg, ps, frame, view, r_capacity=2048):
+    """Binning state of the dense-contract op (raster_dense.cu, bit-exact against the reference kernels in test_gpu_raster.py)
+    for one frame/view of a PackedSequence at its CURRENT parameters."""
+    from skelsplat_b200 import rasterizer as R
+    J = cfg.n_joints
+    dims = ps.dims.cpu().numpy(); tf = ps.tanfov.cpu().numpy()
+    W, H = int(dims[view, 0]), int(dims[view, 1])
+    means = ps.xyz[frame:frame + 1].contiguous()
+    scales = torch.exp(ps.scaling[frame:frame + 1]).contiguous()
+    rots = torch.nn.functional.normalize(ps.rotation[frame:frame + 1], dim=-1).contiguous()
+    opac = torch.sigmoid(ps.opacity[frame:frame + 1]).contiguous()
+    feats = torch.eye(J, device=DEV)
+    _, radii, _, st = R.rasterize_batched(means, scales, rots, opac, feats, ps.viewmatrix[view].reshape(1, 4, 4), ps.projmatrix[view].reshape(1, 4, 4),
+                                          W, H, float(tf[view, 0]), float(tf[view, 1]), r_capacity=r_capacity, render_invdepth=False)
+    return st.parse(0), (means, scales, rots, opac, W, H, float(tf[view, 0]), float(tf[view, 1]))
+
+
+@pytest.mark.parametrize("name", ["h36m", "h36m-occ", "panoptic", "occlusion-person", "occlusion-person-8v"])
+def test_fused_kernel_binning_is_bit_exact(name):
+    """North-star level 1 on the kernel that sets the headline: the fused optimiser's OWN tile lists (closed-form sorted
+    positions, optimizer.cu phase B), dumped through ssb_optimize_frames_debug, equal the dense op's point_list / active tiles /
+    tile ranges bit for bit -- at step 0 (initial state) and at a later Adam step (the state the kernel itself produced), for
+    every slot of the step group incl. the 8-view rig's alternating views -- and, where oracle/_ref is present, the UNMODIFIED
+    reference kernels' sorted point list and ranges."""
+    from oracle import ref_rasterizer as refr
+    cfg = configs.get_config(name)
+    seq = synthetic.make_sequence(cfg, 3, seed=41)
+    poses_init = np.stack([f.pose_3d_init for f in seq.frames]); poses_2d = np.stack([f.poses_2d for f in seq.frames])
+    host = trainer.pack_host(cfg, seq.cameras, poses_init, poses_2d)
+    variant = opipe.VARIANT_OF[cfg.rendering]
+    for step, frame in ((0, 0), (0, 2), (7, 1)):
+        ps = trainer.pack_sequence(cfg, seq.cameras, poses_init, poses_2d, DEV, host=host)
+        if step:
+            trainer.optimize_packed(ps, iterations=step * cfg.accumulation_steps)       # parameters at the start of Adam step `step`
+        state_at_step = [t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity)]
+        ps0 = trainer.pack_sequence(cfg, seq.cameras, poses_init, poses_2d, DEV, host=host)
+        slots = trainer.debug_binning(ps0, frame=frame, step=step)
+        assert len(slots) == cfg.accumulation_steps
+        for k, sl in enumerate(slots):
+            assert sl["view"] == (step * cfg.accumulation_steps + k) % cfg.nviews and sl["status"] == 0
+            for dst, src in zip((ps.xyz, ps.scaling, ps.rotation, ps.opacity), state_at_step):
+                dst.copy_(src)
+            dn, (means, scales, rots, opac, W, H, tfx, tfy) = _dense_binning(cfg, ps, frame, sl["view"])
+            assert sl["R"] == dn["R"] and sl["n_active"] == dn["n_active"] and sl["R"] > 0
+            assert np.array_equal(sl["point_list"], dn["point_list"])
+            assert np.array_equal(sl["inv_pos"], dn["inv_pos"])
+            assert np.array_equal(sl["tile_ids"], dn["tile_ids"])
+            assert np.array_equal(sl["tile_starts"], dn["tile_ranges"][:, 0])
+            ends = np.concatenate([sl["tile_starts"][1:], [sl["R"]]])
+            assert np.array_equal(ends, dn["tile_ranges"][:, 1])
+            if refr.available(variant):
+                J = cfg.n_joints
+                e = torch.Tensor([]); bg = torch.zeros(32, device=DEV)
+                cam = seq.cameras[sl["view"]]
+                tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+                Rn, _, _, geom, binning, img, _ = refr.rasterize_forward(
+                    variant, bg, means[0], e, opac[0].reshape(-1, 1), scales[0], rots[0], 1.0, e, tt(cam.world_view_transform),
+                    tt(cam.full_proj_transform), tfx, tfy, H, W, torch.eye(J, device=DEV).reshape(J, 1, J), 0, tt(cam.camera_center))
+                rs = refr.RefState(geom, binning, img, Rn, J, W, H, variant).parse()
+                assert Rn == sl["R"]
+                assert np.array_equal(rs["point_list"], sl["point_list"])
+                dense_ranges = np.zeros_like(rs["ranges"])
+                dense_ranges[sl["tile_ids"], 0] = sl["tile_starts"]; dense_ranges[sl["tile_ids"], 1] = ends
+                assert np.array_equal(rs["ranges"], dense_ranges)

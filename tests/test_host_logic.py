@@ -80,8 +80,7 @@ def test_heatmap_sigma_uses_the_python_side_covariance_not_ewa():
     seq = synthetic.make_sequence(cfg, 1, seed=0)
     fr = seq.frames[0]
     _, scal, rot, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
-    cov = heatmaps.covariance_3d(scal[0], rot[0])
-    s1, s2 = heatmaps.heatmap_sigmas(fr.pose_3d_init, seq.cameras, cov)
+    s1, s2 = heatmaps.heatmap_sigmas(fr.pose_3d_init, seq.cameras, scal[0], rot[0])
     cam = seq.cameras[0]
     z = (fr.pose_3d_init @ cam.R_w2c.T + cam.t)[:, 2]
     sx = math.exp(3.0) * cam.K[0, 0] / z
@@ -161,7 +160,7 @@ def test_closed_form_sorted_positions_equal_the_reference_sort(name, seed):
     order of the reference's stable (tile | depth) radix sort -- checked here against the C oracle's sort on random,
     overlapping, partly culled Gaussians (equal depths included)."""
     from oracle import rast
-    from skelsplat_b200 import binning
+    from tests import mirror_binning as binning
     from tests.util import raster_case
     cfg = small_config(configs.get_config(name), 2)
     case = raster_case(cfg, seed=seed, n_views=1, big=(seed != 3))
@@ -187,7 +186,7 @@ def test_row_band_contains_every_contributing_pixel():
     """Exactness of the row culling: brute force over pixels with the reference's fp32 power expression (forward.cu:352-364)
     never finds a contributing pixel (power >= -5.55, the cut used with opacity <= 1) outside the band, for isotropic, elongated,
     rotated, tiny and huge splats."""
-    from skelsplat_b200 import binning
+    from tests import mirror_binning as binning
     rng = np.random.default_rng(0)
     f = np.float32
     checked = 0
@@ -219,7 +218,7 @@ def test_fused_one_hot_backward_equals_the_reference_backward():
     constants applied once) against the C oracle of the reference's forward + per-channel backward fed with the l2_gaussian
     gradient: same image, loss, N and per-Gaussian gradients."""
     from oracle import rast
-    from skelsplat_b200 import fused_math
+    from tests import mirror_fused_math as fused_math
     from tests.util import raster_case, relerr
     cfg = small_config(configs.H36M, 8)
     case = raster_case(cfg, seed=5, n_views=1, big=True)
@@ -255,7 +254,7 @@ def test_fused_one_hot_backward_equals_the_reference_backward():
 def test_adam_mirror_matches_torch_adam():
     """The in-kernel Adam (host fp64 step sizes rounded to fp32, eps = 1e-15 added AFTER the bias-corrected sqrt) against
     torch.optim.Adam on the CPU, including the noise-level gradients that eps = 1e-15 turns into full-size steps."""
-    from skelsplat_b200 import fused_math
+    from tests import mirror_fused_math as fused_math
     rng = np.random.default_rng(0)
     n = 64
     p0 = rng.normal(0, 100, n).astype(np.float32)
@@ -279,7 +278,7 @@ def test_adam_mirror_matches_torch_adam():
 def test_closed_form_sorted_positions_on_random_rectangles():
     """Same property without a renderer: for arbitrary tile rectangles (empty, 1 x N, nested, identical, disjoint) and depths with
     ties, the closed form equals a stable sort of the emitted pairs by (tile id, depth bits)."""
-    from skelsplat_b200 import binning
+    from tests import mirror_binning as binning
     rng = np.random.default_rng(7)
     gx = 40
     for trial in range(60):
