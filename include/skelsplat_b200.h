@@ -184,9 +184,10 @@ typedef struct ssb_opt_config {
     int   max_unrolled_list;    /* tuning knob (same arithmetic, different fp32 summation order): tile lists of 5 Gaussians take the unrolled
                                    register-resident path (0 = default = 5) or the chunked generic path (4) */
     int   resident_record_slots;/* tuning knob (bit-identical results): slots of a step group whose per-(tile,Gaussian) records are resident
-                                   in shared memory at once.  0 = auto: all of them when two CTAs per SM fit, else half (the tile phase then
-                                   runs twice per Adam step) when that keeps two CTAs per SM, else all in one 1024-thread CTA per SM.
-                                   accumulation_steps or accumulation_steps/2 force a choice. */
+                                   in shared memory at once.  0 = default = accumulation_steps (all of them; two 512-thread CTAs per SM when
+                                   they fit, else one 1024-thread CTA); accumulation_steps/2 (4 slots only): the tile phase runs twice per
+                                   Adam step over half the record storage, which keeps two CTAs per SM up to r_capacity 1024 -- measured
+                                   slower on B200 for every shipped shape, kept as a knob. */
 } ssb_opt_config;
 
 /* lr_xyz_host: [iterations+1] learning rate of the xyz group at iteration i (host-computed in fp64

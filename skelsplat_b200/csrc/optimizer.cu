@@ -959,12 +959,14 @@ static int optimize_frames_impl(const ssb_opt_config* cfg, int n_frames, const s
     p.dbg = dbg_out; p.dbg_frame = dbg_frame; p.dbg_step = dbg_step;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int slots = cfg->accumulation_steps;
-    // Launch shape.  Two 512-thread CTAs per SM whenever their shared memory fits (227 KB/SM; static + 1 KB reserved per CTA
-    // = 17 KB): with all slots' records resident if possible, else (4 slots only) with the records of two slots at a time;
-    // beyond that one 1024-thread CTA per SM.  32 warps/SM either way.
+    // Launch shape.  Two 512-thread CTAs per SM when their shared memory fits (227 KB/SM; static + 1 KB reserved per CTA =
+    // 17 KB) with all slots' records resident, else one 1024-thread CTA per SM: 32 warps/SM either way.  The third shape --
+    // two 512-thread CTAs with the records of two slots at a time (HALVES = 2) -- keeps two CTAs up to r_capacity 1024, but
+    // measured 4 % SLOWER than the single 1024-thread CTA on the Panoptic shape (5 550 vs 5 784 frames/s, bit-identical
+    // results; profiles/README.md) and 2-7 % slower where both fit, so it is only taken on request (resident_record_slots).
     auto fits2 = [&](int halves) { return SSB_OPT_MIN_CTAS * (opt_dyn_smem(slots, cfg->r_capacity, halves) + 17 * 1024) <= 227 * 1024; };
     if (cfg->resident_record_slots != 0 && cfg->resident_record_slots != slots && !(slots == 4 && cfg->resident_record_slots == 2)) return SSB_ERR_INVALID;
-    const int halves = cfg->resident_record_slots ? slots / cfg->resident_record_slots : (fits2(1) ? 1 : ((slots == 4 && fits2(2)) ? 2 : 1));
+    const int halves = cfg->resident_record_slots ? slots / cfg->resident_record_slots : 1;
     const bool big = !fits2(halves);
     const size_t smem = opt_dyn_smem(slots, cfg->r_capacity, halves);
 #define SSB_LAUNCH_OPT_K(S, NTH, HV)                                                                              \

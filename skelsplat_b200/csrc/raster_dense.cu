@@ -230,39 +230,42 @@ constexpr int FILL_THREADS = 512;
 
 // 256-bit global store (STG.E.256, new on sm_100): measured 7.23 TB/s for a pure fill at 148x64 CTAs x 512 threads
 // vs 5.99 TB/s for the 128-bit version at 148x8 x 256 (scripts/fillbench.cu; cudaMemsetAsync reaches 7.18 TB/s).
-__device__ __forceinline__ void store_zero_256(float* q) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "l"(q), "f"(0.0f) : "memory");
+__device__ __forceinline__ void store_zero_256(float* q, float z) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" :: "l"(q), "f"(z) : "memory");
 }
 
-__device__ __forceinline__ void fill_zero(float* __restrict__ p, size_t n, size_t g, size_t stride) {
+// z = 0, or NaN for a view whose (Gaussian,tile) pairs outgrew r_capacity: its tile lists are truncated, so instead of a
+// plausible-looking wrong image the caller gets one that poisons every reduction over it (no host sync needed to notice).
+__device__ __forceinline__ void fill_zero(float* __restrict__ p, size_t n, size_t g, size_t stride, float z) {
     size_t head = ((32 - (reinterpret_cast<uintptr_t>(p) & 31)) & 31) >> 2;      // floats before 32-B alignment
     if (head > n) head = n;
-    if (g < head) p[g] = 0.f;
+    if (g < head) p[g] = z;
     float* p8 = p + head;
     const size_t n8 = (n - head) >> 3;
     size_t i = g;
     for (; i + stride < n8; i += 2 * stride) {      // 2 independent 32-B stores in flight per thread
-        store_zero_256(p8 + 8 * i);
-        store_zero_256(p8 + 8 * (i + stride));
+        store_zero_256(p8 + 8 * i, z);
+        store_zero_256(p8 + 8 * (i + stride), z);
     }
-    for (; i < n8; i += stride) store_zero_256(p8 + 8 * i);
+    for (; i < n8; i += stride) store_zero_256(p8 + 8 * i, z);
     const size_t tail = head + (n8 << 3) + g;       // < 8 floats left
-    if (g < 8 && tail < n) p[tail] = 0.f;
+    if (g < 8 && tail < n) p[tail] = z;
 }
 
 __global__ void __launch_bounds__(FILL_THREADS)
-fill_zero_kernel(ssb_cameras cams, int C, float* __restrict__ out_color, const int64_t* __restrict__ color_offsets,
-                 float* __restrict__ out_invdepth, const int64_t* __restrict__ invdepth_offsets)
+fill_zero_kernel(ssb_cameras cams, int C, StateLayout L, const char* __restrict__ state, float* __restrict__ out_color,
+                 const int64_t* __restrict__ color_offsets, float* __restrict__ out_invdepth, const int64_t* __restrict__ invdepth_offsets)
 {
     const int b = blockIdx.y;
+    const float z = cfield<int>(state + (size_t)b * L.total, L, SSB_F_HEADER)[2] ? __int_as_float(0x7fc00000) : 0.0f;
     const int cam = b % cams.n_views;
     const int W = cams.dims ? cams.dims[2 * cam] : cams.W0;
     const int H = cams.dims ? cams.dims[2 * cam + 1] : cams.H0;
     const size_t HW = (size_t)H * W;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    fill_zero(out_color + (color_offsets ? color_offsets[b] : (int64_t)b * C * (int64_t)cams.H0 * cams.W0), (size_t)C * HW, g, stride);
+    fill_zero(out_color + (color_offsets ? color_offsets[b] : (int64_t)b * C * (int64_t)cams.H0 * cams.W0), (size_t)C * HW, g, stride, z);
     if (out_invdepth)
-        fill_zero(out_invdepth + (invdepth_offsets ? invdepth_offsets[b] : (int64_t)b * (int64_t)cams.H0 * cams.W0), HW, g, stride);
+        fill_zero(out_invdepth + (invdepth_offsets ? invdepth_offsets[b] : (int64_t)b * (int64_t)cams.H0 * cams.W0), HW, g, stride, z);
 }
 
 template <int C>
@@ -676,7 +679,8 @@ int ssb_rasterize_forward(int n_frames, const ssb_gaussians* g, const ssb_camera
     const long long work = ((long long)g->C * Wmax * Hmax / 8 + 2 * FILL_THREADS - 1) / (2 * FILL_THREADS);
     if (fx > work) fx = (int)work;
     fx = fx < 1 ? 1 : fx;
-    fill_zero_kernel<<<dim3(fx, B), FILL_THREADS, 0, stream>>>(*cams, g->C, out_color, color_offsets, out_invdepth, invdepth_offsets);
+    fill_zero_kernel<<<dim3(fx, B), FILL_THREADS, 0, stream>>>(*cams, g->C, L, (const char*)state, out_color, color_offsets, out_invdepth,
+                                                               invdepth_offsets);
     if (g->P > 0) {
         int G = (148 * 8 + B - 1) / B;
         G = G < 4 ? 4 : (G > 256 ? 256 : G);

@@ -25,7 +25,46 @@ import torch.nn as nn
 
 from . import lib as _L
 
-DEFAULT_R_CAPACITY = 2048
+import os
+
+DEFAULT_R_CAPACITY = int(os.environ.get("SKELSPLAT_B200_R_CAPACITY", 2048))     # (Gaussian,tile) pairs per view of the drop-in op
+MAX_R_CAPACITY = 1 << 14                                                        # ssb_rasterize_forward's upper bound
+
+
+class _OverflowWatch:
+    """Capacity overflow of the drop-in op, made loud WITHOUT a per-render host sync: the forward kernels NaN-fill the image of
+    an overflowed view (so every loss over it is NaN), and the 32-byte state header is copied to pinned host memory behind
+    the kernels; backward -- by which time the copy has long completed -- reads it and raises."""
+    N = 64
+
+    def __init__(self):
+        self.slots = None
+        self.i = 0
+
+    def post(self, state_buf):
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        if self.slots is None:
+            self.slots = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(self.N)]
+        self.i = (self.i + 1) % self.N
+        host, ev = self.slots[self.i]
+        host.copy_(state_buf[:32].view(torch.int32), non_blocking=True)
+        ev.record()
+        return (self.i, host, ev, state_buf.data_ptr())
+
+    @staticmethod
+    def check(ticket, rcap):
+        if ticket is None:
+            return
+        _, host, ev, _ = ticket
+        ev.synchronize()
+        if int(host[2]) != 0:
+            raise _L.SkelSplatLibraryError(
+                f"rasteriser capacity exceeded: this view needs {int(host[7])} (Gaussian,tile) pairs, r_capacity is {rcap}; the rendered image was "
+                f"NaN-filled.  Raise skelsplat_b200.rasterizer.DEFAULT_R_CAPACITY (or SKELSPLAT_B200_R_CAPACITY) up to {MAX_R_CAPACITY}")
+
+
+_overflow_watch = _OverflowWatch()
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -189,7 +228,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         vm = _f32c(rs.viewmatrix).reshape(1, 4, 4)
         pm = _f32c(rs.projmatrix).reshape(1, 4, 4)
         color, radii, invd, st = rasterize_batched(m3, sc, ro, op, feats, vm, pm, W, H, rs.tanfovx, rs.tanfovy,
-                                                   rs.scale_modifier, cv, rs.antialiasing)
+                                                   rs.scale_modifier, cv, rs.antialiasing, r_capacity=DEFAULT_R_CAPACITY)
+        ctx.overflow_ticket = _overflow_watch.post(st.buf)
         if rs.debug:
             torch.cuda.synchronize()
             st.check()
@@ -206,6 +246,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         if ctx.empty or grad_out_color is None:
             return (None,) * 10
         rs, st = ctx.rs, ctx.st
+        _OverflowWatch.check(ctx.overflow_ticket, st.rcap)
         m3, sc, ro, cv, op, feats, vm, pm = ctx.saved_tensors
         H, W = int(rs.image_height), int(rs.image_width)
         g = rasterize_batched_backward(st, m3, sc, ro, op, feats, vm, pm, W, H, rs.tanfovx, rs.tanfovy,

@@ -241,16 +241,79 @@ def optimize_packed(ps: PackedSequence, iterations=None, r_capacity=None, final_
     return ps.xyz, final_loss
 
 
+def dense_roi_heatmaps(ps: PackedSequence, frame):
+    """The frame's GT heatmaps as the dense [J,H,W] tensors of the reference contract, scattered from the ROI patches on the GPU."""
+    cfg = ps.cfg
+    dims = ps.dims.cpu().numpy(); rect = ps.roi_rect[frame].cpu().numpy(); off = ps.roi_offset[frame].cpu().numpy()
+    out = []
+    for v in range(cfg.nviews):
+        hm = torch.zeros((cfg.n_joints, int(dims[v, 1]), int(dims[v, 0])), dtype=torch.float32, device=ps.xyz.device)
+        for j in range(cfg.n_joints):
+            x0, y0, w, h = (int(a) for a in rect[v, j])
+            hm[j, y0:y0 + h, x0:x0 + w] = ps.roi_data[int(off[v, j]):int(off[v, j]) + w * h].reshape(h, w)
+        out.append(hm)
+    return out
+
+
+def dense_fallback(ps: PackedSequence, frames, init, iterations=None, final_loss=None):
+    """Frames whose (Gaussian,tile) lists outgrow the fused kernel's shared-memory ceiling (MAX_R_CAPACITY pairs per view: a
+    close-up, or splats grown very large) are optimised through the dense drop-in surface instead -- train.py's own loop on
+    the dense rasteriser op (capacity 16 384 pairs), the fused loss kernels and torch Adam: the same algorithm, ~10^4 x slower
+    per frame, so one such frame does not cost the batch its results.  ``init`` = (xyz, scaling, rotation, opacity) of those
+    frames.  Returns the indices (into ``frames``) that could not be optimised even so (their poses are set to NaN)."""
+    from types import SimpleNamespace
+    from . import rasterizer as _R
+    from .training import optimise_frame_dropin
+    cfg = ps.cfg
+    cams = [SimpleNamespace(uid=v) for v in range(cfg.nviews)]
+    vm, pm = ps.viewmatrix.cpu().numpy(), ps.projmatrix.cpu().numpy()
+    dims, tf = ps.dims.cpu().numpy(), ps.tanfov.cpu().numpy()
+    import math
+    for v, c in enumerate(cams):
+        c.image_width, c.image_height = int(dims[v, 0]), int(dims[v, 1])
+        c.FoVx, c.FoVy = 2.0 * math.atan(float(tf[v, 0])), 2.0 * math.atan(float(tf[v, 1]))
+        c.world_view_transform, c.full_proj_transform = vm[v].reshape(4, 4), pm[v].reshape(4, 4)
+        c.camera_center = np.linalg.inv(vm[v].reshape(4, 4).T)[:3, 3].astype(np.float32)
+    failed = []
+    saved = _R.DEFAULT_R_CAPACITY
+    _R.DEFAULT_R_CAPACITY = _R.MAX_R_CAPACITY
+    try:
+        for n, f in enumerate(frames.tolist()):
+            fr = SimpleNamespace(pose_3d_init=init[0][n].cpu().numpy(), poses_2d=None)
+            try:
+                st = optimise_frame_dropin(fr, cams, cfg, heatmaps_dense=dense_roi_heatmaps(ps, f), device=ps.xyz.device, iterations=iterations,
+                                           init_state=(init[1][n], init[2][n]), return_state=True, spatial_lr_scale=ps.spatial_lr_scale)
+                if not torch.isfinite(st[0]).all():
+                    raise _L.SkelSplatLibraryError("non-finite result (dense op capacity exceeded)")
+                ps.xyz[f] = st[0]; ps.scaling[f] = st[1]; ps.rotation[f] = st[2]; ps.opacity[f] = st[3].reshape(-1)
+            except _L.SkelSplatLibraryError:
+                ps.xyz[f] = float("nan")
+                failed.append(n)
+            if final_loss is not None:
+                final_loss[f] = float("nan")          # the dense loop does not report it
+    finally:
+        _R.DEFAULT_R_CAPACITY = saved
+    return failed
+
+
 def retry_overflowed(ps: PackedSequence, bad, init_bad, rcap, iterations=None, final_loss=None):
     """Re-run ONLY the frames ``bad`` (indices into ps) from their initial state ``init_bad`` = (xyz, scaling, rotation, opacity)
     with the capacity doubled until they fit; results are written into ps in place.  Exact: a frame's result does not depend
-    on the capacity it ran with, nor on the other frames of the launch."""
+    on the capacity it ran with, nor on the other frames of the launch.  Frames that outgrow even MAX_R_CAPACITY go through
+    ``dense_fallback``; only if that fails too is an error raised -- after every other frame's result is in place, naming the
+    failed frame indices (``err.failed_frames``)."""
     cfg = ps.cfg
     lr = xyz_lr_table(cfg, ps.spatial_lr_scale, cfg.iterations if iterations is None else iterations)
     cur = tuple(t.contiguous() for t in init_bad)
     while bad.numel():
         if rcap >= MAX_R_CAPACITY:
-            raise _L.SkelSplatLibraryError(f"{bad.numel()} frame(s) exceeded r_capacity={rcap} (Gaussian,tile) pairs per view")
+            failed = dense_fallback(ps, bad, cur, iterations, final_loss)
+            if failed:
+                err = _L.SkelSplatLibraryError(f"frame(s) {[int(bad[i]) for i in failed]} exceeded r_capacity={rcap} (Gaussian,tile) pairs per view "
+                                               "in the fused optimiser and the dense fallback's capacity too; every other frame's result is valid")
+                err.failed_frames = [int(bad[i]) for i in failed]
+                raise err
+            return
         rcap = min(2 * rcap, MAX_R_CAPACITY)
         oc = make_opt_config(cfg, rcap, iterations)
         sub = PackedSequence(cfg=cfg, n_frames=int(bad.numel()), xyz=cur[0].clone(), scaling=cur[1].clone(), rotation=cur[2].clone(),

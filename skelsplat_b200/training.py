@@ -31,13 +31,16 @@ class TorchCamera:
         self.camera_center = torch.from_numpy(cam.camera_center).to(device)
 
 
-def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", iterations=None, modules=None):
+def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", iterations=None, modules=None, init_state=None,
+                          return_state=False, spatial_lr_scale=None):
     """One frame through the drop-in API; returns final xyz [J,3] float32 numpy.
 
+    ``frame`` needs ``pose_3d_init`` and ``poses_2d`` (the latter only to build the GT heatmaps when ``heatmaps_dense`` is None).
     ``modules``: optional (GaussianModel, render_functions, losses, consistency_losses) to run the same loop body on another
     implementation of the same surface -- the tests pass the REFERENCE's own classes and functions here (tests/ref_import.py),
     which is how "the reference's Python runs unchanged on the drop-in packages" is checked."""
     iterations = cfg.iterations if iterations is None else iterations
+    extent = cameras_extent(cams) if spatial_lr_scale is None else spatial_lr_scale
     GM, rfuncs, loss_table, cons_table = modules if modules is not None else (GaussianModel, render_functions, losses, consistency_losses)
     ref_surface = modules is not None
     opt = SimpleNamespace(position_lr_init=cfg.position_lr_init, position_lr_final=cfg.position_lr_final,
@@ -52,11 +55,14 @@ def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", 
         pcd = SimpleNamespace(points=pts, colors=np.zeros_like(pts), normals=np.zeros_like(pts))
         cam_infos = [SimpleNamespace(image_name=f"cam{c.uid}") for c in cams]
         opt.exposure_lr_init, opt.exposure_lr_final, opt.exposure_lr_delay_steps, opt.exposure_lr_delay_mult, opt.iterations = 0.01, 0.001, 0, 0.0, iterations
-        gaussians.create_from_pcd(pcd, cam_infos, cameras_extent(cams), cfg.opacity_on, cfg.scaling, cfg.n_joints, cfg.scaling_modifier, cfg.name)
+        gaussians.create_from_pcd(pcd, cam_infos, extent, cfg.opacity_on, cfg.scaling, cfg.n_joints, cfg.scaling_modifier, cfg.name)
     else:
         gaussians = GM(1, "default", device)
-        gaussians.create_from_pcd(np.asarray(frame.pose_3d_init, np.float32), cams, cameras_extent(cams), cfg.opacity_on, cfg.scaling,
+        gaussians.create_from_pcd(np.asarray(frame.pose_3d_init, np.float32), cams, extent, cfg.opacity_on, cfg.scaling,
                                   cfg.n_joints, cfg.scaling_modifier, cfg.name)
+    if init_state is not None:      # (scaling_raw [J,3], rotation_raw [J,4]): start from a given raw state (dense fallback of the fused path)
+        with torch.no_grad():
+            gaussians._scaling.copy_(torch.as_tensor(init_state[0]).to(device)); gaussians._rotation.copy_(torch.as_tensor(init_state[1]).to(device))
     gaussians.training_setup(opt)
     tcams = [TorchCamera(c, device) for c in cams]
     if heatmaps_dense is None:
@@ -68,7 +74,8 @@ def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", 
     consistency_criterion = cons_table[cfg.consistency_loss]
     bg = torch.tensor([0, 0, 0], dtype=torch.float32, device=device)
     accumulated_grads = torch.zeros((len(tcams),) + tuple(gaussians.get_xyz.shape), device=device)
-    poses_2d = torch.as_tensor(np.asarray(frame.poses_2d))
+    # gt_2d argument of the loss table's signature (utils/loss_utils.py:67,86): only the never-configured soft-argmax losses read it
+    poses_2d = torch.as_tensor(np.asarray(frame.poses_2d)) if frame.poses_2d is not None else torch.zeros((len(cams), cfg.n_joints, 2))
     for iteration in range(1, iterations + 1):
         gaussians.update_learning_rate(iteration)
         idx = (iteration - 1) % len(tcams)
@@ -85,4 +92,6 @@ def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", 
             with torch.no_grad():
                 gaussians.optimizer.step()
                 gaussians.optimizer.zero_grad(set_to_none=True)
+    if return_state:
+        return tuple(t.detach().clone() for t in (gaussians._xyz, gaussians._scaling, gaussians._rotation, gaussians._opacity))
     return gaussians._xyz.detach().cpu().numpy().copy()

@@ -9,8 +9,9 @@ It needs oracle/_ref/libref_rast_*.so (built here from /root/reference by oracle
                          inverse depth, final_T, n_contrib) + the reference backward's gradients for a
                          seeded dL (two runs: the reference's atomics make it non-reproducible, the
                          second run records its own spread)
-  opt_<config>.npz       final joint positions of the restated train.py loop on the reference kernels
-                         (500 iterations) for seeded synthetic frames, plus two re-runs of every frame (the reference's own spread)
+  opt_<config>.npz       final joint positions (500 iterations) of 64 seeded synthetic frames per config from the reference's own
+                         Python on the reference's own kernels (see make_opt), plus two re-runs of the first 8 frames (the
+                         reference's own spread); configs: h36m, h36m-occ, panoptic, occlusion-person, occlusion-person-8v
 """
 import argparse
 import os
@@ -67,31 +68,55 @@ def make_raster(variant, cfg_name, out):
     print("wrote raster", variant)
 
 
-def make_opt(cfg_name, out, n_frames=4, seed=1, iterations=500):
+def make_opt(cfg_name, out, n_frames=64, seed=1, iterations=500, n_rerun=8):
+    """Final poses of the reference pipeline for `n_frames` seeded synthetic frames: the reference's OWN Python (GaussianModel,
+    render_*, l2_loss_gaussian, limb_3d_consistency_loss, torch Adam -- imported unmodified, tests/ref_import.py) on the
+    reference's OWN kernels (oracle/_ref), under train.py's iteration body (skelsplat_b200/training.py restates it; the loop
+    itself needs hydra).  GT heatmaps: the ROI specification (heatmaps.py), the same input our paths consume.  Falls back to
+    the restated oracle loop (oracle/pipeline.py, pinned to the reference Python by tests/test_reference_python.py) when the
+    staged reference Python is absent.  The first `n_rerun` frames are run two more times: the reference's own spread."""
+    from tests import ref_import
+    from skelsplat_b200.training import optimise_frame_dropin
     cfg = configs.get_config(cfg_name)
     seq = synthetic.make_sequence(cfg, n_frames, seed=seed)
     ext = cameras_extent(seq.cameras)
+    via = "reference-python" if ref_import.available() else "restated-loop"
+    if via == "reference-python":
+        ref = ref_import.load("ref")
+        mods = (ref.gaussian_model.GaussianModel, ref.gaussian_renderer.render_functions, ref.utils.losses, ref.utils.consistency_losses)
     finals, reruns = [], []
     for fi, frame in enumerate(seq.frames):
         _, scal0, rot0, _ = trainer.initial_raw_state(cfg, frame.pose_3d_init[None])
         rois = heatmaps.generate_heatmap_rois(frame.pose_3d_init, frame.poses_2d, seq.cameras, scal0[0], rot0[0])
         dense = [torch.from_numpy(heatmaps.rois_to_dense(rois, v)).to(DEV) for v in range(cfg.nviews)]
-        finals.append(opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend="ref", device=DEV, iterations=iterations))
-        # the reference's backward uses unordered fp32 atomics: two more runs of the SAME frame record its own spread
-        reruns.append(np.stack([opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend="ref", device=DEV, iterations=iterations)
-                                for _ in range(2)]))
-    np.savez_compressed(os.path.join(out, f"opt_{cfg_name}.npz"), ref_xyz=np.stack(finals), ref_xyz_reruns=np.stack(reruns),
-                        seed=seed, n_frames=n_frames, iterations=iterations,
+        if via == "reference-python":
+            run = lambda: optimise_frame_dropin(frame, seq.cameras, cfg, heatmaps_dense=dense, device=DEV, iterations=iterations, modules=mods)
+        else:
+            run = lambda: opipe.optimise_frame(frame, seq.cameras, cfg, ext, dense, backend="ref", device=DEV, iterations=iterations)
+        finals.append(run())
+        if fi < n_rerun:        # the reference's backward uses unordered fp32 atomics: two more runs of the SAME frame record its own spread
+            reruns.append(np.stack([run() for _ in range(2)]))
+    np.savez_compressed(os.path.join(out, f"opt_{cfg_name}.npz"), ref_xyz=np.stack(finals).astype(np.float32), ref_xyz_reruns=np.stack(reruns).astype(np.float32),
+                        seed=seed, n_frames=n_frames, iterations=iterations, n_rerun=n_rerun, via=via,
                         init_xyz=np.stack([f.pose_3d_init for f in seq.frames]), gt_xyz=np.stack([f.pose_3d_gt for f in seq.frames]))
-    print("wrote opt", cfg_name)
+    mine = trainer.optimize_sequence(seq, DEV, iterations=iterations)        # calibration printout only (not stored)
+    ref_xyz, rr = np.stack(finals), np.stack(reruns)
+    dev = np.linalg.norm(mine - ref_xyz, axis=-1)
+    spread = np.linalg.norm(rr - ref_xyz[:n_rerun, None], axis=-1)
+    print("wrote opt", cfg_name, via, "| fused vs golden: max %.4f p99 %.4f median %.5f mm | reference spread: max %.4f p99 %.4f median %.5f mm | mpjpe delta %.5f"
+          % (dev.max(), np.percentile(dev, 99), np.median(dev), spread.max(), np.percentile(spread, 99), np.median(spread),
+             trainer.mpjpe(mine, np.stack([f.pose_3d_gt for f in seq.frames])) - trainer.mpjpe(ref_xyz, np.stack([f.pose_3d_gt for f in seq.frames]))), flush=True)
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "golden"))
+    ap.add_argument("--frames", type=int, default=64, help="frames per config (SURVEY.md 8d: parity sets of 64)")
+    ap.add_argument("--skip-raster", action="store_true")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
-    for variant, name in (("h36m", "h36m"), ("panoptic", "panoptic"), ("op", "occlusion-person")):
-        make_raster(variant, name, args.out)
-    for name in ("h36m", "h36m-occ", "panoptic", "occlusion-person"):
-        make_opt(name, args.out)
+    if not args.skip_raster:
+        for variant, name in (("h36m", "h36m"), ("panoptic", "panoptic"), ("op", "occlusion-person")):
+            make_raster(variant, name, args.out)
+    for name in ("h36m", "h36m-occ", "panoptic", "occlusion-person", "occlusion-person-8v"):      # 8v: the stale/zero-slot accumulation quirk at 500 iterations
+        make_opt(name, args.out, n_frames=args.frames)
