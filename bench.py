@@ -573,8 +573,17 @@ def bench_dropin_and_losses(torch, cfg, seq, dev, hbm_peak):
     def ssim_train():
         a.grad = None
         fused_ssim(a, b).backward()
-    out["fused_ssim_5x1x1500x1500"] = {"train_iter_ms": round(ev(ssim_train), 3),
-                                       "inference_ms": round(ev(lambda: fused_ssim(a.detach(), b, train=False)), 3),
+    n_px = 5 * 1500 * 1500
+    t_train, t_inf = ev(ssim_train), ev(lambda: fused_ssim(a.detach(), b, train=False))
+    # compulsory HBM bytes: inference reads 2 images; a training iteration reads 2 images and writes 3 derivative maps (forward),
+    # reads them + the 2 images and writes the gradient (backward): 4*(2) and 4*(2+3+3+2+1) bytes per pixel.  The kernel's own
+    # floor is the fp32 FMA pipe: 110 FMA per pixel for the separable 11-tap window over 5 moments (+66 in backward).
+    out["fused_ssim_5x1x1500x1500"] = {"train_iter_ms": round(t_train, 3), "inference_ms": round(t_inf, 3),
+                                       "inference_frac_of_hbm_peak": round(8 * n_px / t_inf / 1e6 / hbm_peak, 3),
+                                       "train_frac_of_hbm_peak": round(44 * n_px / t_train / 1e6 / hbm_peak, 3),
+                                       "fma_floor_ms": {"inference": round(110 * n_px / 35.8e12 * 1e3, 4), "train": round(176 * n_px / 35.8e12 * 1e3, 4),
+                                                        "note": "fp32 FMA peak 71.6 TFLOP/s measured (profiles/r01_microbench.json)"},
+                                       "same_box_reference": "see `bench.py --impl reference` line, key fused_ssim_5x1x1500x1500",
                                        "published_rtx3080ti_ms": {"train_iter": 3.0, "inference": 1.3}}
     return out
 
@@ -720,6 +729,7 @@ def run_reference(args):
         if dist is not None:
             dist.destroy_process_group()
         return
+    ssim_ref = reference_fused_ssim(torch, dev) if use_ref else None
     kind = "reference" if use_ref else "port"
     sample = (f"{len(secs)} frames x {iters} iterations per rank, one frame per step: UNMODIFIED reference CUDA kernels (oracle/_ref, built from the reference's "
               "forward.cu/backward.cu/rasterizer_impl.cu for sm_100a) on the GPU + the reference's torch ops (clamp, l2_gaussian, autograd, Adam) "
@@ -733,10 +743,37 @@ def run_reference(args):
             "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                              "device": dev},
             "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "clocks": clocks, "configs": extras}
+            "clocks": clocks, "configs": extras, "fused_ssim_5x1x1500x1500": ssim_ref}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def reference_fused_ssim(torch, dev):
+    """Same-box baseline for the SSIM library surface: fused-ssim's OWN kernels (submodules/fused-ssim/ssim.cu compiled
+    unmodified, oracle/_ref/fused_ssim_cuda.so) under its own wrapper, at the shape its README plots (B=5, CH=1, 1500x1500)."""
+    try:
+        from oracle import ref_ssim
+        if not ref_ssim.available():
+            return {"unavailable": "oracle/_ref/fused_ssim_cuda.so not built (make -C oracle ref_ssim)"}
+        fs = ref_ssim.load()
+        a = torch.rand(5, 1, 1500, 1500, device=dev).requires_grad_(True); b = torch.rand(5, 1, 1500, 1500, device=dev)
+
+        def ev(fn, reps=10):
+            fn(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+            return float(np.median(ts))
+
+        def train():
+            a.grad = None
+            fs.fused_ssim(a, b).backward()
+        return {"train_iter_ms": round(ev(train), 3), "inference_ms": round(ev(lambda: fs.fused_ssim(a.detach(), b, train=False)), 3),
+                "kernels": "fusedssimCUDA / fusedssim_backwardCUDA (reference, unmodified) + torch mean / expand"}
+    except Exception as e:      # noqa: BLE001
+        return {"error": repr(e)[:300]}
 
 
 _RESULT_OUT = None

@@ -165,6 +165,16 @@ int ssb_fused_ssim_backward(int B, int CH, int H, int W, float C1, float C2, con
                             const float* dL_dmap, const float* dm_dmu1, const float* dm_dsigma1_sq,
                             const float* dm_dsigma12, float* dL_dimg1, void* stream);
 
+/* The form fused_ssim() actually consumes -- map.mean() (fused_ssim/__init__.py:34-41) -- without materialising the map or
+ * dL/dmap: forward writes the mean over the pixels at least `crop` away from the border (0: padding "same"; 5: "valid") to
+ * *mean_out (device) and, when the dm_* pointers are given, the three derivative maps; backward takes dL/dmean as a device
+ * scalar.  workspace: ssb_fused_ssim_mean_workspace_bytes() bytes (per-warp partial sums, summed in a fixed order). */
+size_t ssb_fused_ssim_mean_workspace_bytes(int B, int CH, int H, int W);
+int ssb_fused_ssim_mean_forward(int B, int CH, int H, int W, float C1, float C2, const float* img1, const float* img2, int crop,
+                                float* mean_out, float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* workspace, void* stream);
+int ssb_fused_ssim_mean_backward(int B, int CH, int H, int W, const float* img1, const float* img2, const float* grad_mean, int crop,
+                                 const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12, float* dL_dimg1, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused per-frame optimiser: the whole train.py:130-233 iteration loop (render one view,
  * l2_gaussian + limb consistency, backward, gradient bookkeeping, Adam every accumulation_steps)

@@ -9,8 +9,9 @@ import bench
 from skelsplat_b200 import configs, trainer
 name, F, rcap = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 cfg = configs.get_config(name)
-seq, host, gt = bench.make_host_batch(cfg, F, seed=100)
-ps = trainer.pack_sequence(cfg, seq.cameras, host["xyz"], None, "cuda", host=host)
+from skelsplat_b200 import setup_gpu
+seq, p2d, init0, gt = bench.make_detection_batch(cfg, F, 0)
+ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, torch.from_numpy(p2d), torch.from_numpy(init0), "cuda")
 init = tuple(t.clone() for t in (ps.xyz, ps.scaling, ps.rotation, ps.opacity))
 ts = []
 for rep in range(3):
@@ -46,7 +47,7 @@ def build_variants(variants):
 
 
 def main(variants):
-    works = [("h36m", 2048, 256), ("occlusion-person-8v", 2048, 512), ("panoptic", 1024, 1024)]
+    works = [("h36m", 2048, 320), ("occlusion-person-8v", 2048, 512), ("panoptic", 1024, 1024)]
     out = {}
     for name, F, rcap in works:
         for i, defs in enumerate(variants):

@@ -1,4 +1,4 @@
-"""Small workloads for ncu captures (developer tool).  usage: profile_target.py opt|dense|loss [frames]"""
+"""Small workloads for ncu captures (developer tool).  usage: profile_target.py opt|dense|loss|ssim [frames] [config]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -11,8 +11,9 @@ dev = "cuda"
 cfg = configs.get_config(sys.argv[3]) if len(sys.argv) > 3 else configs.H36M
 if what == "opt":
     F = int(sys.argv[2]) if len(sys.argv) > 2 else 592
-    seq, host, gt = bench.make_host_batch(cfg, F, seed=100)
-    ps = trainer.pack_sequence(cfg, seq.cameras, host["xyz"], None, dev, host=host)
+    from skelsplat_b200 import setup_gpu
+    seq, p2d, init, gt = bench.make_detection_batch(cfg, F, 0)
+    ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, torch.from_numpy(p2d), torch.from_numpy(init), dev)
     trainer.optimize_packed(ps, check=False)
     torch.cuda.synchronize()
 elif what == "dense":
@@ -24,4 +25,12 @@ elif what == "loss":
     r = torch.rand(17, 1000, 1000, device=dev, requires_grad=True); g = torch.rand(17, 1000, 1000, device=dev)
     for _ in range(3):
         l, _ = LU.l2_loss_gaussian(r, g, None, want_error=False); l.backward()
+    torch.cuda.synchronize()
+elif what == "ssim":
+    from fused_ssim import fused_ssim
+    a = torch.rand(5, 1, 1500, 1500, device=dev).requires_grad_(True); b = torch.rand(5, 1, 1500, 1500, device=dev)
+    for _ in range(2):
+        a.grad = None
+        fused_ssim(a, b).backward()
+        fused_ssim(a.detach(), b, train=False)
     torch.cuda.synchronize()

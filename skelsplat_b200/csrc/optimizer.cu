@@ -55,6 +55,18 @@ __device__ unsigned long long g_list_hist[24];      // tiles by list length (ind
 #else
 #define SSB_PHASE_MARK(i)
 #endif
+// developer experiments (scripts/gpu_tune_opt.py; never in the product build): upper bounds on what removing the GT loads /
+// a cheaper exp could buy.  Results are WRONG with either.
+#ifdef SSB_EXP_NOGT
+#define SSB_GT_LOAD(p) (0.25f)
+#else
+#define SSB_GT_LOAD(p) __ldg(p)
+#endif
+#ifdef SSB_EXP_FASTEXP
+#define SSB_EXPF(x) __expf(x)
+#else
+#define SSB_EXPF(x) expf(x)
+#endif
 constexpr int MAXJ = 20;
 constexpr int MAXV = 8;
 constexpr int MAX_SLOTS = 4;
@@ -153,7 +165,7 @@ __device__ __forceinline__ bool pair_alpha_hoisted(float gpy, float conz, float 
     const float power = __fmaf_rn(t, -0.5f, -__fmul_rn(dy, dxcy));
     if (power > 0.0f) return false;
     if (power < -5.55f && opac <= 1.0f) return false;
-    G = expf(power);
+    G = SSB_EXPF(power);
     alpha = fminf(ALPHA_MAX, __fmul_rn(opac, G));
     return !(alpha < ALPHA_MIN);
 }
@@ -237,7 +249,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = __ldg(gptr[u] + (pass0 + q) * gw2[u]);
+                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = SSB_GT_LOAD(gptr[u] + (pass0 + q) * gw2[u]);
                 }
             }
             float pyf[PP];
@@ -333,7 +345,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
 #pragma unroll
             for (int q = 0; q < PP; q++) {
                 gtv[q] = 0.f;
-                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = __ldg(gp + (pass0 + q) * gw2);
+                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = SSB_GT_LOAD(gp + (pass0 + q) * gw2);
             }
 #pragma unroll
             for (int q = 0; q < PP; q++) {
@@ -345,7 +357,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
                     t = __fmaf_rn(dx, dxcx, t);
                     const float power = __fmaf_rn(t, -0.5f, -__fmul_rn(dy, dxcy));
                     if (!(power > 0.0f) && !(power < -5.55f && A.z <= 1.0f)) {
-                        const float G = expf(power);
+                        const float G = SSB_EXPF(power);
                         const float alpha = fminf(ALPHA_MAX, __fmul_rn(A.z, G));
                         if (!(alpha < ALPHA_MIN)) {
                             pair_accumulate(acc, acc[6], acc[7], dx, dy, G, 1.0f, alpha - gtv[q], 0.0f, gtv[q]);   // err = rendered - GT
@@ -400,8 +412,8 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
         for (int pass = vlo; pass <= vhi; pass++) {
             const unsigned gm = gmask >> pass;
             float gt0 = 0.f, gt1 = 0.f;
-            if (gm & 1u) gt0 = __ldg(gptr[0] + pass * gw2[0]);
-            if (gm & 0x100u) gt1 = __ldg(gptr[1] + pass * gw2[1]);
+            if (gm & 1u) gt0 = SSB_GT_LOAD(gptr[0] + pass * gw2[0]);
+            if (gm & 0x100u) gt1 = SSB_GT_LOAD(gptr[1] + pass * gw2[1]);
             const int py = ly0 + 2 * pass;
             if (py < H) {
                 const float pyf = (float)py;

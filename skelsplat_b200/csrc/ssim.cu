@@ -3,128 +3,378 @@
 // Same contract as the reference's fused-ssim extension (submodules/fused-ssim/ssim.cu:187-444):
 // forward writes the SSIM map and, when training, the three partial-derivative maps
 // dm/dmu1, dm/dsigma1^2, dm/dsigma12; backward returns dL/dimg1 as three Gaussian convolutions of
-// dL/dmap * dm/d{...}.  Design differences: one CTA per (32x32 tile, image plane) instead of a serial
-// loop over channels (B*CH x more CTAs in flight), all five moments convolved in one horizontal and
-// one vertical pass out of a single staging of the two 42x42 halo tiles (the reference re-stages
-// and re-synchronises per moment: 5 x (flush, conv-x, conv-y) with 20 block syncs; here 3).
+// dL/dmap * dm/d{...}.
+//
+// Design (round 2).  The reference (and round 1 here) stage a 42x42 halo tile in shared memory and run both 1-D passes out of
+// it: ~80 scalar shared-memory loads per output pixel, which bounds the kernel at ~15-20 % of the HBM roof.  Here every WARP
+// owns a 32-column strip and marches down the rows (no block-level barrier at all):
+//   * horizontal pass: the row's 42 input pixels of both images go through a per-warp (u,v)-interleaved row buffer, so one
+//     LDS.64 per tap delivers the (u,v) pair; the five moments are accumulated with PACKED fp32 math (FFMA2 / FMUL2,
+//     `fma.rn.f32x2`, new on sm_100): (mu1,mu2) and (E[x^2],E[y^2]) as pairs, E[xy] alone -- 6 instructions per tap;
+//   * vertical pass: the last 11 horizontal results live in a REGISTER ring (the row loop is unrolled by 11 so every ring
+//     index is static): 3 instructions per tap, no shared memory, and a finished output row every input row;
+//   * the next input row's global loads are issued before the current row's math (one row of software prefetch);
+//   * `fused_ssim()` only ever consumes map.mean(): the MEAN variants reduce the map in the kernel (per-warp partial sums,
+//     summed in a fixed order in fp64 by a tiny second kernel) and take dL/dmap as the scalar it is, so neither the map nor
+//     dL/dmap ever touches HBM (train step: 495 MB instead of 675 MB at 5x1x1500x1500).
+// Per-pixel epilogue uses two IEEE reciprocals (1/A, 1/B) instead of the reference's seven divisions; results agree with
+// the reference's kernels to ~1e-6 relative (tests/test_reference_python.py, tests/test_gpu_losses.py).
 #include "api_internal.h"
 
 namespace ssb {
 
-constexpr int SS_T = 32;            // output tile edge
-constexpr int SS_R = 5;             // window radius
-constexpr int SS_H = SS_T + 2 * SS_R;   // halo tile edge (42)
-constexpr int SS_THREADS = 256;
+constexpr int SS_R = 5;              // window radius
+constexpr int SS_WARPS = 8;          // warps (= 32-column strips) per CTA
+constexpr int SS_ROWS_MAX = 96;      // output rows per warp strip: chosen per launch (ss_rows) so that the strips fill whole waves
+constexpr int SS_BUFW = 48;          // row buffer width (>= 32 + 2*SS_R)
+constexpr int SS_NB = 8;             // row buffers per warp (power of two): SS_NB - 1 rows of cp.async in flight
 
-// 11-tap normalised Gaussian, sigma = 1.5: the literal constants of the reference (ssim.cu:9-19)
-__constant__ float c_gauss[11] = {
-    0.001028380123898387f, 0.0075987582094967365f, 0.036000773310661316f, 0.10936068743467331f,
-    0.21300552785396576f, 0.26601171493530273f, 0.21300552785396576f, 0.10936068743467331f,
-    0.036000773310661316f, 0.0075987582094967365f, 0.001028380123898387f};
-
-__device__ __forceinline__ float load_zero_pad(const float* __restrict__ plane, int y, int x, int H, int W) {
-    return (x >= 0 && y >= 0 && x < W && y < H) ? __ldg(plane + (size_t)y * W + x) : 0.0f;
+// 11-tap normalised Gaussian, sigma = 1.5: the literal constants of the reference (ssim.cu:9-19); symmetric
+#define SS_G0 0.001028380123898387f
+#define SS_G1 0.0075987582094967365f
+#define SS_G2 0.036000773310661316f
+#define SS_G3 0.10936068743467331f
+#define SS_G4 0.21300552785396576f
+#define SS_G5 0.26601171493530273f
+__device__ __forceinline__ constexpr float ss_g(int k) {
+    return (k == 0 || k == 10) ? SS_G0 : (k == 1 || k == 9) ? SS_G1 : (k == 2 || k == 8) ? SS_G2 : (k == 3 || k == 7) ? SS_G3
+         : (k == 4 || k == 6) ? SS_G4 : SS_G5;
 }
 
-__global__ void __launch_bounds__(SS_THREADS)
-ssim_fwd_kernel(int H, int W, float C1, float C2, const float* __restrict__ img1, const float* __restrict__ img2,
+// ---- packed fp32 pairs (one 64-bit register pair; FFMA2 / FMUL2 issue ONE instruction for two IEEE fp32 operations)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// 1/x for x in [1e-5, 1e4] (the SSIM denominators: >= C1 or ~C2 > 0): approximate reciprocal + one Newton step, <= 1 ulp, no
+// denormal slow path (__frcp_rn compiles to a call with one)
+__device__ __forceinline__ float rcp_nr(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+// keeps a loop-invariant value in its register: without it ptxas re-derives lane / warp / block indices from the special
+// registers in every unrolled row (~40 extra instructions per row)
+#define SS_KEEP(v) asm volatile("" : "+r"(v))
+
+// cp.async (LDGSTS): 4-byte global -> shared copies that bypass the register file; src_bytes = 0 zero-fills (zero padding,
+// rows / columns outside the image).  Each warp keeps SS_NB - 1 input rows in flight: with one row of register prefetch the
+// kernel was bound by memory LATENCY (16 warps x 1 row x ~340 B in flight per SM ~ 0.7 TB/s by Little's law).
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ float ld0(const float* __restrict__ plane, int y, int x, int H, int W) {
+    return ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) ? __ldg(plane + (size_t)y * W + x) : 0.0f;
+}
+
+// TRAIN: also write the three derivative maps.  MEAN: do not write the map; accumulate it (inside the `crop` border) into
+// per-warp partial sums instead.
+template <bool TRAIN, bool MEAN>
+__global__ void __launch_bounds__(SS_WARPS * 32)
+ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restrict__ img1, const float* __restrict__ img2,
                 float* __restrict__ ssim_map, float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
-                float* __restrict__ dm_dsigma12)
+                float* __restrict__ dm_dsigma12, int crop, float* __restrict__ partials)
 {
-    __shared__ float s1[SS_H][SS_H + 1], s2[SS_H][SS_H + 1];
-    __shared__ float h[5][SS_H][SS_T + 1];     // horizontal pass of x, y, x^2, y^2, xy
+    __shared__ __align__(16) float2 s_row[SS_WARPS][SS_NB][SS_BUFW];  // (u, v) interleaved; a ring of SS_NB rows per warp
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SS_KEEP(lane); SS_KEEP(warp);
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const float* p1 = img1 + plane;
-    const float* p2 = img2 + plane;
-    const int x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < SS_H * SS_H; i += SS_THREADS) {
-        const int ly = i / SS_H, lx = i - ly * SS_H;
-        s1[ly][lx] = load_zero_pad(p1, y0 + ly - SS_R, x0 + lx - SS_R, H, W);
-        s2[ly][lx] = load_zero_pad(p2, y0 + ly - SS_R, x0 + lx - SS_R, H, W);
-    }
-    __syncthreads();
-    for (int i = tid; i < SS_H * SS_T; i += SS_THREADS) {
-        const int ly = i / SS_T, lx = i - ly * SS_T;
-        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+    int x0 = (blockIdx.x * SS_WARPS + warp) * 32, y0 = blockIdx.y * rows;
+    SS_KEEP(x0); SS_KEEP(y0);
+    float local_sum = 0.f;
+    if (x0 < W) {
+        const int n_out = min(rows, H - y0);
+        const int n_in = n_out + 2 * SS_R;
+        const int xa = x0 - SS_R + lane, xb = xa + 32;                 // the lane's two input columns (xb only for lane < 10)
+        const int px = x0 + lane;
+        // column validity etc.: loop-invariant flags in one register
+        int flags = ((unsigned)xa < (unsigned)W ? 1 : 0) | ((lane < 2 * SS_R && (unsigned)xb < (unsigned)W) ? 2 : 0) | (px < W ? 4 : 0) |
+                    ((px >= crop && px < W - crop) ? 8 : 0) | (lane < 2 * SS_R ? 16 : 0);
+        SS_KEEP(flags);
+#define ca (flags & 1)
+#define cb (flags & 2)
+#define cw (flags & 4)
+#define cc (flags & 8)
+#define lo10 (flags & 16)
+        float2* mybuf = &s_row[warp][0][lane];                         // the lane's slot in ring row 0
+        f32x2 gg[6];
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float g = c_gauss[k], u = s1[ly][lx + k], v = s2[ly][lx + k];
-            a += g * u; b += g * v; aa += g * (u * u); bb += g * (v * v); ab += g * (u * v);
-        }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = aa; h[3][ly][lx] = bb; h[4][ly][lx] = ab;
-    }
-    __syncthreads();
-    for (int i = tid; i < SS_T * SS_T; i += SS_THREADS) {
-        const int ly = i / SS_T, lx = i - ly * SS_T;
-        const int px = x0 + lx, py = y0 + ly;
-        if (px >= W || py >= H) continue;
-        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+        for (int k = 0; k < 6; k++) gg[k] = pack2(ss_g(k), ss_g(k));
+        f32x2 ring_m[11], ring_e[11];                                  // (mu1, mu2), (E[x^2], E[y^2]) after the horizontal pass
+        float ring_x[11];                                              // E[xy]
+        // input element (y0 - 5 + row, xa) of both images; clamped to the plane when outside (never read then: src size 0)
+        const float* p1 = img1 + plane;
+        const float* p2 = img2 + plane;
+        size_t o = plane + (size_t)y0 * W + px;                        // output element of the current output row
+        auto issue_row = [&](int row) {                                // input row `row` of this strip -> ring slot row % SS_NB
+            const int y = y0 - SS_R + row;
+            const bool yv = (unsigned)y < (unsigned)H && row < n_in;
+            const ptrdiff_t base = yv ? (ptrdiff_t)y * W : 0;
+            float2* dst = mybuf + (row & (SS_NB - 1)) * SS_BUFW;
+            const bool va_ = yv && ca, vb_ = yv && cb;
+            const ptrdiff_t ia = va_ ? base + xa : 0, ib_ = vb_ ? base + xb : 0;
+            cp_async4(&dst->x, p1 + ia, va_);
+            cp_async4(&dst->y, p2 + ia, va_);
+            if (lo10) {
+                cp_async4(&dst[32].x, p1 + ib_, vb_);
+                cp_async4(&dst[32].y, p2 + ib_, vb_);
+            }
+            cp_async_commit();
+        };
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float g = c_gauss[k];
-            mu1 += g * h[0][ly + k][lx]; mu2 += g * h[1][ly + k][lx];
-            e11 += g * h[2][ly + k][lx]; e22 += g * h[3][ly + k][lx]; e12 += g * h[4][ly + k][lx];
+        for (int r = 0; r < SS_NB - 1; r++) issue_row(r);
+#pragma unroll 1
+        for (int ib = 0; ib < n_in; ib += 11) {
+#pragma unroll
+            for (int ii = 0; ii < 11; ii++) {
+                const int i = ib + ii;
+                if (i < n_in) {                                        // warp-uniform
+                    cp_async_wait<SS_NB - 2>();                        // this lane's copies of row i have landed ...
+                    __syncwarp();                                      // ... and so have the other lanes'; slot (i - 1) is free
+                    issue_row(i + SS_NB - 1);                          // (an empty group past the last row keeps the count uniform)
+                    const float2* buf = mybuf + (i & (SS_NB - 1)) * SS_BUFW;
+                    // horizontal pass: 11 taps, (u,v) pairs straight from shared memory
+                    f32x2 hm = 0ull, he = 0ull;
+                    float hx = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 11; k++) {
+                        const float2 uv = buf[k];
+                        const f32x2 p = pack2(uv.x, uv.y);
+                        const f32x2 g2 = gg[k <= 5 ? k : 10 - k];
+                        hm = fma2(g2, p, hm);
+                        he = fma2(g2, mul2(p, p), he);
+                        hx = fmaf(ss_g(k), uv.x * uv.y, hx);
+                    }
+                    ring_m[ii] = hm; ring_e[ii] = he; ring_x[ii] = hx;
+                    if (i >= 2 * SS_R) {
+                        // vertical pass over the register ring: the oldest row sits at (ii + 1) % 11
+                        f32x2 vm = 0ull, ve = 0ull;
+                        float e12 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 11; k++) {
+                            const int r = (ii + 1 + k) % 11;
+                            const f32x2 g2 = gg[k <= 5 ? k : 10 - k];
+                            vm = fma2(g2, ring_m[r], vm);
+                            ve = fma2(g2, ring_e[r], ve);
+                            e12 = fmaf(ss_g(k), ring_x[r], e12);
+                        }
+                        if (cw) {
+                            float mu1, mu2, e11, e22;
+                            unpack2(vm, mu1, mu2); unpack2(ve, e11, e22);
+                            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
+                            const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
+                            const float Cc = 2.0f * mu1_mu2 + C1, D = 2.0f * sigma12 + C2;
+                            const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
+                            const float rA = rcp_nr(A), rB = rcp_nr(B), rAB = rA * rB;
+                            const float m = Cc * D * rAB;
+                            if (MEAN) {
+                                const int py = y0 + i - 2 * SS_R;
+                                if (cc && py >= crop && py < H - crop) local_sum += m;
+                            } else {
+                                ssim_map[o] = m;
+                            }
+                            if (TRAIN) {
+                                // d ssim / d mu1, d sigma1^2, d sigma12  (ssim.cu:264-283, the same algebra with 1/A, 1/B factored out)
+                                dm_dmu1[o] = 2.0f * rAB * (mu2 * (D - Cc) + mu1 * (Cc * D) * (rB - rA));
+                                dm_dsigma1_sq[o] = -m * rB;
+                                dm_dsigma12[o] = 2.0f * Cc * rAB;
+                            }
+                        }
+                        o += W;
+                    }
+                }
+            }
         }
-        const float sigma1_sq = e11 - mu1 * mu1, sigma2_sq = e22 - mu2 * mu2, sigma12 = e12 - mu1 * mu2;
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
-        const float Cc = 2.0f * mu1_mu2 + C1, D = 2.0f * sigma12 + C2;
-        const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
-        const size_t o = plane + (size_t)py * W + px;
-        ssim_map[o] = (Cc * D) / (A * B);
-        if (dm_dmu1) {
-            dm_dmu1[o] = (mu2 * 2.0f * D) / (A * B) - (mu2 * 2.0f * Cc) / (A * B) - (mu1 * 2.0f * Cc * D) / (A * A * B) + (mu1 * 2.0f * Cc * D) / (A * B * B);
-            dm_dsigma1_sq[o] = (-Cc * D) / (A * B * B);
-            dm_dsigma12[o] = (2.0f * Cc) / (A * B);
-        }
+        cp_async_wait<0>();
+#undef ca
+#undef cb
+#undef cw
+#undef cc
+#undef lo10
+    }
+    if (MEAN) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_sum += __shfl_xor_sync(0xFFFFFFFFu, local_sum, o);
+        if (lane == 0)
+            partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (gridDim.x * SS_WARPS) + blockIdx.x * SS_WARPS + warp] = local_sum;
     }
 }
 
-__global__ void __launch_bounds__(SS_THREADS)
-ssim_bwd_kernel(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
-                const float* __restrict__ dL_dmap, const float* __restrict__ dm_dmu1,
-                const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
+// Fixed-order fp64 sum of the per-warp partial sums -> mean (one CTA; deterministic).
+__global__ void __launch_bounds__(256)
+ssim_mean_finalize_kernel(const float* __restrict__ partials, long long n, double inv_count, float* __restrict__ out)
+{
+    __shared__ double s[256];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) a += (double)partials[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = (float)(s[0] * inv_count);
+}
+
+// Backward: dL/dimg1 = conv(dL dm/dmu1) + 2 img1 conv(dL dm/dsigma1^2) + img2 conv(dL dm/dsigma12)   (ssim.cu:288-366).
+// MEAN: dL/dmap is the scalar *grad_scalar * scale inside the crop border and 0 outside: never materialised -- the border is
+// zero-filled by the copies and the scalar is applied after the convolutions.
+constexpr int SS_BUFW_B = 44;        // >= 32 + 2*SS_R
+// dynamic shared memory per CTA: per warp a ring of SS_NB input rows (float4) + SS_NB rows of (img1, img2) at the output pixels
+constexpr size_t SS_BWD_SMEM = (size_t)SS_WARPS * SS_NB * (SS_BUFW_B * sizeof(float4) + 32 * sizeof(float2));
+template <bool MEAN>
+__global__ void __launch_bounds__(SS_WARPS * 32)
+ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const float* __restrict__ img2,
+                const float* __restrict__ dL_dmap, const float* __restrict__ grad_scalar, float scale, int crop,
+                const float* __restrict__ dm_dmu1, const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
                 float* __restrict__ dL_dimg1)
 {
-    __shared__ float s[3][SS_H][SS_H + 1];      // dL_dmap * dm_d{mu1, sigma1_sq, sigma12}
-    __shared__ float h[3][SS_H][SS_T + 1];
+    extern __shared__ __align__(16) unsigned char ss_dyn[];
+    float4 (*s_row)[SS_NB][SS_BUFW_B] = reinterpret_cast<float4 (*)[SS_NB][SS_BUFW_B]>(ss_dyn);     // (dm/dmu1, dm/dsigma1^2, dm/dsigma12, dL/dmap)
+    float2 (*s_pix)[SS_NB][32] = reinterpret_cast<float2 (*)[SS_NB][32]>(ss_dyn + (size_t)SS_WARPS * SS_NB * SS_BUFW_B * sizeof(float4));
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SS_KEEP(lane); SS_KEEP(warp);
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < SS_H * SS_H; i += SS_THREADS) {
-        const int ly = i / SS_H, lx = i - ly * SS_H;
-        const int y = y0 + ly - SS_R, x = x0 + lx - SS_R;
-        const float dl = load_zero_pad(dL_dmap + plane, y, x, H, W);
-        s[0][ly][lx] = dl * load_zero_pad(dm_dmu1 + plane, y, x, H, W);
-        s[1][ly][lx] = dl * load_zero_pad(dm_dsigma1_sq + plane, y, x, H, W);
-        s[2][ly][lx] = dl * load_zero_pad(dm_dsigma12 + plane, y, x, H, W);
-    }
-    __syncthreads();
-    for (int i = tid; i < SS_H * SS_T; i += SS_THREADS) {
-        const int ly = i / SS_T, lx = i - ly * SS_T;
-        float a = 0.f, b = 0.f, c = 0.f;
+    int x0 = (blockIdx.x * SS_WARPS + warp) * 32, y0 = blockIdx.y * rows;
+    SS_KEEP(x0); SS_KEEP(y0);
+    if (x0 >= W) return;
+    const float gs = MEAN ? __ldg(grad_scalar) * scale : 1.f;
+    const int n_out = min(rows, H - y0);
+    const int n_in = n_out + 2 * SS_R;
+    const int xa = x0 - SS_R + lane, xb = xa + 32;
+    const int px = x0 + lane;
+    // a column contributes if it is inside the image and (MEAN) inside the crop border
+    int flags = ((xa >= crop && xa < W - crop) ? 1 : 0) | ((lane < 2 * SS_R && xb >= crop && xb < W - crop) ? 2 : 0) | (px < W ? 4 : 0) |
+                (lane < 2 * SS_R ? 8 : 0);
+    SS_KEEP(flags);
+#define ca (flags & 1)
+#define cb (flags & 2)
+#define cw (flags & 4)
+#define lo10 (flags & 8)
+    float4* mybuf = &s_row[warp][0][lane];
+    float2* mypix = &s_pix[warp][0][lane];
+    f32x2 gg[6];
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float g = c_gauss[k];
-            a += g * s[0][ly][lx + k]; b += g * s[1][ly][lx + k]; c += g * s[2][ly][lx + k];
+    for (int k = 0; k < 6; k++) gg[k] = pack2(ss_g(k), ss_g(k));
+    const float* q1 = dm_dmu1 + plane;
+    const float* q2 = dm_dsigma1_sq + plane;
+    const float* q3 = dm_dsigma12 + plane;
+    const float* q0 = MEAN ? nullptr : dL_dmap + plane;
+    const float* i1 = img1 + plane;
+    const float* i2 = img2 + plane;
+    // one commit group per row index: the input row `row` of the strip AND the two image values the output row finished in the
+    // same iteration (row - 10) needs -- so the epilogue never waits on a global load
+    auto issue_row = [&](int row) {
+        const int y = y0 - SS_R + row;
+        const bool yv = y >= crop && y < H - crop && row < n_in;
+        const ptrdiff_t base = yv ? (ptrdiff_t)y * W : 0;
+        float4* dst = mybuf + (row & (SS_NB - 1)) * SS_BUFW_B;
+        const bool va_ = yv && ca, vb_ = yv && cb;
+        const ptrdiff_t ia = va_ ? base + xa : 0, ib_ = vb_ ? base + xb : 0;
+        cp_async4(&dst->x, q1 + ia, va_); cp_async4(&dst->y, q2 + ia, va_); cp_async4(&dst->z, q3 + ia, va_);
+        if (!MEAN) cp_async4(&dst->w, q0 + ia, va_);
+        if (lo10) {
+            cp_async4(&dst[32].x, q1 + ib_, vb_); cp_async4(&dst[32].y, q2 + ib_, vb_); cp_async4(&dst[32].z, q3 + ib_, vb_);
+            if (!MEAN) cp_async4(&dst[32].w, q0 + ib_, vb_);
         }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = c;
-    }
-    __syncthreads();
-    for (int i = tid; i < SS_T * SS_T; i += SS_THREADS) {
-        const int ly = i / SS_T, lx = i - ly * SS_T;
-        const int px = x0 + lx, py = y0 + ly;
-        if (px >= W || py >= H) continue;
-        float a = 0.f, b = 0.f, c = 0.f;
+        const int yo = y0 + row - 2 * SS_R;
+        const bool vo = row >= 2 * SS_R && row < n_in && cw;
+        const ptrdiff_t io = vo ? (ptrdiff_t)yo * W + px : 0;
+        float2* pd = mypix + (row & (SS_NB - 1)) * 32;
+        cp_async4(&pd->x, i1 + io, vo); cp_async4(&pd->y, i2 + io, vo);
+        cp_async_commit();
+    };
+    f32x2 ring_ab[11];
+    float ring_c[11];
 #pragma unroll
-        for (int k = 0; k < 11; k++) {
-            const float g = c_gauss[k];
-            a += g * h[0][ly + k][lx]; b += g * h[1][ly + k][lx]; c += g * h[2][ly + k][lx];
+    for (int r = 0; r < SS_NB - 1; r++) issue_row(r);
+    size_t o = plane + (size_t)y0 * W + px;
+#pragma unroll 1
+    for (int ib = 0; ib < n_in; ib += 11) {
+#pragma unroll
+        for (int ii = 0; ii < 11; ii++) {
+            const int i = ib + ii;
+            if (i < n_in) {
+                cp_async_wait<SS_NB - 2>();
+                __syncwarp();
+                issue_row(i + SS_NB - 1);
+                const float4* buf = mybuf + (i & (SS_NB - 1)) * SS_BUFW_B;
+                f32x2 hab = 0ull;
+                float hc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; k++) {
+                    float4 t = buf[k];
+                    if (!MEAN) { t.x *= t.w; t.y *= t.w; t.z *= t.w; }
+                    hab = fma2(gg[k <= 5 ? k : 10 - k], pack2(t.x, t.y), hab);
+                    hc = fmaf(ss_g(k), t.z, hc);
+                }
+                ring_ab[ii] = hab; ring_c[ii] = hc;
+                if (i >= 2 * SS_R) {
+                    f32x2 vab = 0ull;
+                    float vc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 11; k++) {
+                        const int r = (ii + 1 + k) % 11;
+                        vab = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[r], vab);
+                        vc = fmaf(ss_g(k), ring_c[r], vc);
+                    }
+                    if (cw) {
+                        float a, b;
+                        unpack2(vab, a, b);
+                        const float2 pix = mypix[(i & (SS_NB - 1)) * 32];
+                        const float v = a + pix.x * 2.0f * b + pix.y * vc;
+                        dL_dimg1[o] = MEAN ? gs * v : v;
+                    }
+                    o += W;
+                }
+            }
         }
-        const size_t o = plane + (size_t)py * W + px;
-        const float pix1 = __ldg(img1 + o), pix2 = __ldg(img2 + o);
-        dL_dimg1[o] = a + pix1 * 2.0f * b + pix2 * c;
     }
+    cp_async_wait<0>();
+#undef ca
+#undef cb
+#undef cw
+#undef lo10
+}
+
+// Rows per warp strip: every strip costs (rows + 10) input rows; the launch runs ceil(strips / resident warps) rounds of
+// equal strips, so pick the height that minimises rounds x (rows + 10)  (148 SMs x 2 CTAs x 8 warps resident).
+static int ss_rows(int B, int CH, int H, int W) {
+    const long long slots = 148LL * 2 * SS_WARPS;
+    const long long cols = (long long)((W + 32 * SS_WARPS - 1) / (32 * SS_WARPS)) * SS_WARPS * B * CH;   // strips per row band (incl. idle warps)
+    long long best_cost = -1; int best = 64;
+    for (int rows = 24; rows <= SS_ROWS_MAX; rows++) {
+        const long long strips = cols * ((H + rows - 1) / rows);
+        const long long cost = ((strips + slots - 1) / slots) * (rows + 2 * SS_R);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+    }
+    return best < H ? best : (H > 0 ? H : 1);
+}
+
+static dim3 ss_grid(int B, int CH, int H, int W, int rows) {
+    return dim3((W + 32 * SS_WARPS - 1) / (32 * SS_WARPS), (H + rows - 1) / rows, B * CH);
+}
+// the mean workspace is sized for the smallest strip height ss_rows() may choose
+static dim3 ss_grid_max(int B, int CH, int H, int W) { return ss_grid(B, CH, H, W, H < 24 ? (H > 0 ? H : 1) : 24); }
+
+template <bool MEAN>
+static cudaError_t ss_launch_bwd(dim3 grid, cudaStream_t st, int H, int W, int rows, const float* img1, const float* img2, const float* dL_dmap,
+                                 const float* grad_scalar, float scale, int crop, const float* d1, const float* d2, const float* d3, float* out) {
+    static bool attr_set = false;      // per instantiation
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(ssim_bwd_kernel<MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_BWD_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ssim_bwd_kernel<MEAN><<<grid, SS_WARPS * 32, SS_BWD_SMEM, st>>>(H, W, rows, img1, img2, dL_dmap, grad_scalar, scale, crop, d1, d2, d3, out);
+    return cudaGetLastError();
 }
 
 }  // namespace ssb
@@ -140,8 +390,11 @@ int ssb_fused_ssim_forward(int B, int CH, int H, int W, float C1, float C2, cons
     if (!img1 || !img2 || !ssim_map) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
-    const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, B * CH);
-    ssim_fwd_kernel<<<grid, SS_THREADS, 0, (cudaStream_t)stream_>>>(H, W, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12);
+    const int rows = ss_rows(B, CH, H, W);
+    const dim3 grid = ss_grid(B, CH, H, W, rows);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (dm_dmu1) ssim_fwd_kernel<true, false><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, 0, nullptr);
+    else ssim_fwd_kernel<false, false><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, ssim_map, nullptr, nullptr, nullptr, 0, nullptr);
     return ssb_set_cuda_error(cudaGetLastError());
 }
 
@@ -153,9 +406,44 @@ int ssb_fused_ssim_backward(int B, int CH, int H, int W, float C1, float C2, con
     if ((size_t)B * CH * H * W == 0) return SSB_OK;
     if (!img1 || !img2 || !dL_dmap || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
-    const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, B * CH);
-    ssim_bwd_kernel<<<grid, SS_THREADS, 0, (cudaStream_t)stream_>>>(H, W, img1, img2, dL_dmap, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1);
+    const int rows = ss_rows(B, CH, H, W);
+    return ssb_set_cuda_error(ss_launch_bwd<false>(ss_grid(B, CH, H, W, rows), (cudaStream_t)stream_, H, W, rows, img1, img2, dL_dmap, nullptr, 0.f, 0,
+                                                   dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1));
+}
+
+size_t ssb_fused_ssim_mean_workspace_bytes(int B, int CH, int H, int W) {
+    const dim3 g = ss_grid_max(B > 0 ? B : 1, CH > 0 ? CH : 1, H > 0 ? H : 1, W > 0 ? W : 1);
+    return (size_t)g.x * g.y * g.z * SS_WARPS * sizeof(float);
+}
+
+int ssb_fused_ssim_mean_forward(int B, int CH, int H, int W, float C1, float C2, const float* img1, const float* img2, int crop,
+                                float* mean_out, float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* workspace, void* stream_) {
+    if (B < 0 || CH < 0 || H < 0 || W < 0 || crop < 0) return SSB_ERR_INVALID;
+    if ((size_t)B * CH * H * W == 0 || H <= 2 * crop || W <= 2 * crop) return SSB_ERR_INVALID;
+    if (!img1 || !img2 || !mean_out || !workspace) return SSB_ERR_INVALID;
+    if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
+    if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
+    const int rows = ss_rows(B, CH, H, W);
+    const dim3 grid = ss_grid(B, CH, H, W, rows);
+    cudaStream_t st = (cudaStream_t)stream_;
+    float* partials = (float*)workspace;
+    if (dm_dmu1) ssim_fwd_kernel<true, true><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, crop, partials);
+    else ssim_fwd_kernel<false, true><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, nullptr, nullptr, nullptr, nullptr, crop, partials);
+    const double count = (double)B * CH * (double)(H - 2 * crop) * (double)(W - 2 * crop);
+    ssim_mean_finalize_kernel<<<1, 256, 0, st>>>(partials, (long long)grid.x * grid.y * grid.z * SS_WARPS, 1.0 / count, mean_out);
     return ssb_set_cuda_error(cudaGetLastError());
+}
+
+int ssb_fused_ssim_mean_backward(int B, int CH, int H, int W, const float* img1, const float* img2, const float* grad_mean, int crop,
+                                 const float* dm_dmu1, const float* dm_dsigma1_sq, const float* dm_dsigma12, float* dL_dimg1, void* stream_) {
+    if (B < 0 || CH < 0 || H < 0 || W < 0 || crop < 0) return SSB_ERR_INVALID;
+    if ((size_t)B * CH * H * W == 0 || H <= 2 * crop || W <= 2 * crop) return SSB_ERR_INVALID;
+    if (!img1 || !img2 || !grad_mean || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) return SSB_ERR_INVALID;
+    if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
+    const double count = (double)B * CH * (double)(H - 2 * crop) * (double)(W - 2 * crop);
+    const int rows = ss_rows(B, CH, H, W);
+    return ssb_set_cuda_error(ss_launch_bwd<true>(ss_grid(B, CH, H, W, rows), (cudaStream_t)stream_, H, W, rows, img1, img2, nullptr, grad_mean,
+                                                  (float)(1.0 / count), crop, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1));
 }
 
 }  // extern "C"

@@ -51,6 +51,7 @@ EXPORTS = [
     "ssb_mark_visible", "ssb_state_field_offset",
     "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency",
     "ssb_fused_ssim_forward", "ssb_fused_ssim_backward",
+    "ssb_fused_ssim_mean_workspace_bytes", "ssb_fused_ssim_mean_forward", "ssb_fused_ssim_mean_backward",
     "ssb_optimize_workspace_bytes", "ssb_optimize_frames", "ssb_optimize_frames_debug",
     "ssb_triangulate_dlt", "ssb_heatmap_roi_rects", "ssb_heatmap_roi_offsets", "ssb_heatmap_roi_fill",
 ]
@@ -86,6 +87,7 @@ def lib():
         L.ssb_backward_scratch_bytes.restype = C.c_size_t
         L.ssb_state_field_offset.restype = C.c_int64
         L.ssb_optimize_workspace_bytes.restype = C.c_size_t
+        L.ssb_fused_ssim_mean_workspace_bytes.restype = C.c_size_t
         for which, struct in enumerate((Gaussians, Cameras, OptConfig)):      # the ctypes mirrors must match the header
             if L.ssb_struct_size(C.c_int(which)) != C.sizeof(struct):
                 raise SkelSplatLibraryError(f"{LIB_PATH}: struct layout mismatch for {struct.__name__} "

@@ -142,36 +142,15 @@ def load_fused_ssim(kernels="ref"):
     kernels="ref": ITS OWN kernels, oracle/_ref/fused_ssim_cuda.so (submodules/fused-ssim/ssim.cu compiled unmodified by
                    `make -C oracle ref_ssim`), or
     kernels="ours": this repo's fused_ssim package's extension surface (fusedssim / fusedssim_backward)."""
-    key = "ssim_" + kernels
-    if key in _cache:
-        return _cache[key]
-    root = ref_root()
-    if root is None:
-        raise RuntimeError("reference Python not available")
-    import torch  # noqa: F401  (libtorch must be loaded before the extension)
+    from oracle import ref_ssim
     if kernels == "ref":
-        so = os.path.join(ROOT, "oracle", "_ref", "fused_ssim_cuda.so")
-        spec = importlib.util.spec_from_file_location("fused_ssim_cuda", so)
-        ext = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(ext)
-    else:
-        import fused_ssim as ours
-        ext = types.ModuleType("fused_ssim_cuda")
-        ext.fusedssim, ext.fusedssim_backward = ours.fusedssim, ours.fusedssim_backward
-    saved = sys.modules.get("fused_ssim_cuda")
-    sys.modules["fused_ssim_cuda"] = ext
-    try:
-        spec = importlib.util.spec_from_file_location(f"refpy_fused_ssim_{kernels}", os.path.join(root, "submodules", "fused-ssim", "fused_ssim", "__init__.py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-    finally:
-        if saved is None:
-            sys.modules.pop("fused_ssim_cuda", None)
-        else:
-            sys.modules["fused_ssim_cuda"] = saved
-    _cache[key] = mod
-    return mod
+        return ref_ssim.load()
+    import fused_ssim as ours
+    ext = types.ModuleType("fused_ssim_cuda")
+    ext.fusedssim, ext.fusedssim_backward = ours.fusedssim, ours.fusedssim_backward
+    return ref_ssim.load(ext, tag="ours")
 
 
 def ref_ssim_available():
-    return ref_root() is not None and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "fused_ssim_cuda.so"))
+    from oracle import ref_ssim
+    return ref_ssim.available()

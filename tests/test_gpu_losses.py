@@ -94,3 +94,22 @@ def test_fused_ssim_identical_images_is_one():
     from fused_ssim import fused_ssim
     x = torch.rand(1, 3, 64, 80, device=DEV)
     assert abs(fused_ssim(x, x.clone()).item() - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 300, 1501), (1, 3, 65, 33), (3, 2, 64, 256), (1, 1, 129, 31)])
+@pytest.mark.parametrize("padding", ["same", "valid"])
+def test_fused_ssim_mean_path_equals_the_map_path(shape, padding):
+    """fused_ssim() reduces the map inside the kernel (the map and dL/dmap never reach HBM); FusedSSIMMap -- the reference's
+    autograd surface, fused_ssim/__init__.py:8-32 -- still materialises it.  Same value and image gradient (summation order
+    aside), incl. strips narrower than a warp, heights that are not multiples of the 64-row strips, and the 'valid' crop."""
+    import fused_ssim as FS
+    g = torch.Generator().manual_seed(4)
+    a = torch.rand(shape, generator=g).to(DEV); b = torch.rand(shape, generator=g).to(DEV)
+    x = a.clone().requires_grad_(True); y = a.clone().requires_grad_(True)
+    v1 = FS.fused_ssim(x, b, padding)
+    v2 = FS.FusedSSIMMap.apply(0.01 ** 2, 0.03 ** 2, y, b, padding, True).mean()
+    assert torch.isclose(v1, v2, rtol=2e-6, atol=1e-7)
+    (3.0 * v1).backward(); (3.0 * v2).backward()
+    assert (x.grad - y.grad).abs().max() <= 1e-6 * y.grad.abs().max() + 1e-12
+    with pytest.raises(RuntimeError, match="train=True"):
+        FS.fused_ssim(a.clone().requires_grad_(True), b, padding, train=False).backward()

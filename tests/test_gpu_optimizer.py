@@ -295,7 +295,7 @@ def test_frames_beyond_the_fused_capacity_fall_back_to_the_dense_path():
     direct = optimise_frame_dropin(big.frames[0], big.cameras, big_cfg, heatmaps_dense=trainer.dense_roi_heatmaps(ps2, 0), device=DEV, iterations=iters)
     assert np.linalg.norm(out[0] - direct, axis=-1).max() < 1e-3
     assert np.linalg.norm(out[0] - pi[0], axis=-1).max() > 0.5    # it was optimised
-    ref = trainer.optimize_sequence(small, DEV, iterations=iters)
+    ref = trainer.optimize_sequence(synthetic.Sequence(cfg=configs.H36M, cameras=big.cameras, frames=small.frames), DEV, iterations=iters)
     assert np.array_equal(out[1:], ref)
 
 

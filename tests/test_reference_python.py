@@ -309,7 +309,7 @@ def test_fused_ssim_against_the_reference_kernels(shape, padding):
     # the reference wrapper runs unchanged on OUR extension surface (drop-in at the fused_ssim_cuda level)
     swapped = ref_import.load_fused_ssim("ours")
     z = a.clone().requires_grad_(True)
-    vs = swapped.fused_ssim(z, b, padding=padding)
-    assert torch.equal(vs, vm)
+    vs = swapped.fused_ssim(z, b, padding=padding)          # their wrapper: map.mean() in torch; ours reduces inside the kernel
+    assert torch.isclose(vs, vm, rtol=2e-6, atol=1e-7)
     vs.backward()
-    assert torch.equal(z.grad, y.grad)
+    assert (z.grad - y.grad).abs().max() <= 1e-6 * y.grad.abs().max() + 1e-12
