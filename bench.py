@@ -231,7 +231,10 @@ def measure_config(torch, dist, name, args, rank, world, local, headline):
         for dst, src in zip((ps.xyz, ps.scaling, ps.rotation, ps.opacity), init_state):
             dst.copy_(src)
 
+    l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > the 126 MB L2
+
     def step_resident(collective=True):
+        l2_flush.zero_()                                   # the step's inputs (factored GT profiles + state) fit in L2: evict them between steps
         reset()
         trainer.optimize_packed(ps, check=False)
         launches[0] += 1
@@ -307,7 +310,7 @@ def measure_config(torch, dist, name, args, rank, world, local, headline):
                           "h2d_bytes_per_step": sum(int(v.numel() * v.element_size()) for v in pinned.values()), "d2h_bytes_per_step": d2h,
                           "ms_per_step": round(ms_roi / steps, 3),
                           "includes": "trainer.StreamingOptimizer.submit: host-prepared GT heatmap ROI patches + initial state cross PCIe every step"}
-    del so, ps, gathered
+    del so, ps, gathered, l2_flush
     torch.cuda.empty_cache()
     return out
 
@@ -442,7 +445,8 @@ def run_ours(args):
                    "frames_over_capacity_all_ranks": main["n_overflowed"], "iterations": cfg.iterations,
                    "adam_steps": cfg.iterations // cfg.accumulation_steps, "loss": "l2_gaussian + 1e-5 limb consistency",
                    "parallelism": f"frame-sharded x{world} (shards of one sequence, one camera rig)" + (", NCCL all_gather of final poses" if world > 1 else ""),
-                   "l2": f"inputs larger than L2: {mb['roi_mb_per_step']:.0f} MB of GT ROIs + state per step vs 126 MB L2 (no flush)",
+                   "l2": f"L2 flushed between steps (a 256 MB fill inside the timed region, ~40 us/step): the step's inputs -- {mb['roi_mb_per_step']:.0f} MB of "
+                         "factored GT heatmap profiles + 0.5 MB of state -- fit in the 126 MB L2",
                    "library": {"ssb_version": int(L.lib().ssb_version()), "source_hash": L.lib().ssb_source_hash().decode()}},
         "e2e": dict(mb["e2e"], includes="trainer.StreamingOptimizer.submit_detections: per step pinned-host -> device copy of the 2D detections + "
                     "initial 3D guess, initial Gaussian state and GT heatmap ROIs generated on the GPU (ssb_heatmap_roi_*), fused optimiser, "

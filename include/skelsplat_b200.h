@@ -203,9 +203,11 @@ typedef struct ssb_opt_config {
 /* lr_xyz_host: [iterations+1] learning rate of the xyz group at iteration i (host-computed in fp64
  * exactly as get_expon_lr_func, utils/general_utils.py:38-71, then rounded as torch does).
  * Per-frame state (updated in place): xyz [F,J,3], scaling_raw [F,J,3], rotation_raw [F,J,4],
- * opacity_raw [F,J].  Cameras as ssb_cameras.  GT heatmap ROIs: roi_rect [F,V,J,4] int32
- * (x0,y0,w,h), roi_offset [F,V,J] int64 into roi_data (float).  Outputs: final_loss [F] (loss of
- * the last iteration) or NULL.  workspace: ssb_optimize_workspace_bytes(). */
+ * opacity_raw [F,J].  Cameras as ssb_cameras.  GT heatmaps as FACTORED ROIs: roi_rect [F,V,J,4] int32
+ * (x0,y0,w,h) and roi_offset [F,V,J] int64 into roi_data (float), where a patch is h + w floats
+ * col[h] | row[w] and the heatmap value at window pixel (a,b) is the fp32 product col[a]*row[b]
+ * (0 outside the window); the patches of one frame must be contiguous in roi_data.  Outputs:
+ * final_loss [F] (loss of the last iteration) or NULL.  workspace: ssb_optimize_workspace_bytes(). */
 size_t ssb_optimize_workspace_bytes(const ssb_opt_config* cfg, int n_frames);
 int ssb_optimize_frames(const ssb_opt_config* cfg, int n_frames, const ssb_cameras* cams,
                         const double* lr_xyz_host,
@@ -232,9 +234,10 @@ int ssb_optimize_frames_debug(const ssb_opt_config* cfg, int n_frames, const ssb
  * P [V,3,4] fp64 projection matrices K[R|t]; poses_2d [F,V,J,2] fp64; out_xyz [F,J,3] fp64 (dehomogenised). */
 int ssb_triangulate_dlt(int n_frames, int V, int J, const double* P, const double* poses_2d, double* out_xyz, void* stream);
 
-/* Pseudo-GT heatmaps as ROI patches.  Replaces generate_heatmaps (utils/general_utils.py:175-304).  Two steps so the
- * caller can size the packed buffer:  (1) rectangles / sigmas / peak positions / patch sizes for every (frame,view,joint);
- * (2) after an exclusive scan of roi_size into roi_offset, fill the normalised patches.
+/* Pseudo-GT heatmaps as factored ROI patches (col[h] | row[w] per patch, see ssb_optimize_frames).  Replaces generate_heatmaps
+ * (utils/general_utils.py:175-304).  Two steps so the caller can size the packed buffer:  (1) rectangles / sigmas / peak
+ * positions / patch sizes (h + w floats) for every (frame,view,joint); (2) after an exclusive scan of roi_size into
+ * roi_offset, fill the profiles.
  * xyz [F,J,3], scaling_raw [F,J,3] (log), rotation_raw [F,J,4], poses_2d [F,V,J,2] fp32;
  * roi_rect [F,V,J,4] int32 (x0,y0,w,h), roi_sigma [F,V,J,2] (sigma_y, sigma_x), roi_center [F,V,J,2] int32 (x,y),
  * roi_size / roi_offset [F,V,J] int64, roi_data fp32. */

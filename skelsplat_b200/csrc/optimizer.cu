@@ -58,9 +58,9 @@ __device__ unsigned long long g_list_hist[24];      // tiles by list length (ind
 // developer experiments (scripts/gpu_tune_opt.py; never in the product build): upper bounds on what removing the GT loads /
 // a cheaper exp could buy.  Results are WRONG with either.
 #ifdef SSB_EXP_NOGT
-#define SSB_GT_LOAD(p) (0.25f)
+#define SSB_GT_COL(p) (0.25f)
 #else
-#define SSB_GT_LOAD(p) __ldg(p)
+#define SSB_GT_COL(p) __ldg(p)        // the profiles are ~25 KB per frame and re-read every iteration: they live in L1 / L2
 #endif
 #ifdef SSB_EXP_FASTEXP
 #define SSB_EXPF(x) __expf(x)
@@ -194,7 +194,7 @@ __device__ __forceinline__ void reduce_store_partial(const float (&acc)[PSTRIDE]
 // range of passes whose row falls inside the patch (columns are pass-invariant for a lane).
 template <int N, int PP>
 __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
-                                          const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
+                                          const float* const* __restrict__ fac_v,
                                           int lx, int ly0, int W, int H, float* __restrict__ part_out, int lane)
 {
     // The loss term is accumulated on every step although only the last one reports it: a second instantiation without it
@@ -205,10 +205,11 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
     // [rlo, rhi] of at least one listed Gaussian (phase A; exact, see there).  The test is a warp-uniform LOOP BOUND, not a
     // per-pass predicate -- the per-pass form cost more than it saved.  ~37 % of the (pass, entry) pairs at H36M scale
     // contain no contributing pixel at all.
-    int gid[N], gw2[N];
-    const float* gptr[N];                                          // the lane's column in row ly0 of patch u (may lie outside it)
+    int gid[N];
+    float grow[N];                                                 // row-profile value of the lane's column in patch u (0 outside it)
+    const float* gptr[N];                                          // column profile of patch u at the lane's row of pass 0 (may lie outside it)
     typedef typename std::conditional<(N > 4), unsigned long long, unsigned>::type mask_t;
-    mask_t gmask = 0;                                              // bit (8u + pass): the lane's pixel of that pass lies in patch u
+    mask_t gmask = 0;                                              // bit (8u + pass): the lane's ROW of that pass lies in patch u
     const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
     int vlo = TILE / 2, vhi = -1;
 #pragma unroll
@@ -224,10 +225,11 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
         int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                 // first pass with ry0 + 2*pass >= 0
         int phi = (roi.w - ry0 + 1) >> 1;                          // first pass with ry0 + 2*pass >= h
         phi = phi > TILE / 2 ? TILE / 2 : phi;
-        if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (mask_t)(((1u << (phi - plo)) - 1u) << plo) << (8 * u);
-        gptr[u] = roi_base + (roi_rel_v[g] + ry0 * roi.z + rx);
+        if (phi > plo) gmask |= (mask_t)(((1u << (phi - plo)) - 1u) << plo) << (8 * u);
+        const float* fp = fac_v[g];                                // col[h] | row[w]
+        grow[u] = ((unsigned)rx < (unsigned)roi.z) ? __ldg(fp + roi.w + rx) : 0.f;
+        gptr[u] = fp + ry0;
         asm volatile("" : "+l"(gptr[u]));   // keep the finished 64-bit pointer (else base + offset is re-derived per load)
-        gw2[u] = 2 * roi.z;
     }
     float accv[N][PSTRIDE];           // [u][6], [u][7] (loss term, count) are used for u == 0 only: see pair_accumulate
 #pragma unroll
@@ -249,7 +251,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = SSB_GT_LOAD(gptr[u] + (pass0 + q) * gw2[u]);
+                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = SSB_GT_COL(gptr[u] + 2 * (pass0 + q)) * grow[u];
                 }
             }
             float pyf[PP];
@@ -320,7 +322,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 // backward of a pixel collapse into one predicated block -- ~45 instead of ~75 instructions per pixel.  Bit-identical to
 // tile_fast<1, PP> (same operations on the same operands, the dropped ones are multiplications by 1 and additions of 0).
 template <int PP>
-__device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4 roi, int roi_rel, const float* __restrict__ roi_base,
+__device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4 roi, const float* __restrict__ fp,
                                          int lx, int ly0, int W, int H, float* __restrict__ part_out, int lane)
 {
     const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
@@ -331,11 +333,12 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
     int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;                     // first pass with ry0 + 2*pass >= 0
     int phi = (roi.w - ry0 + 1) >> 1;                              // first pass with ry0 + 2*pass >= h
     phi = phi > TILE / 2 ? TILE / 2 : phi;
-    unsigned gmask = 0u;                                           // bit pass: the lane's pixel of that pass lies in the patch
-    if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask = ((1u << (phi - plo)) - 1u) << plo;
-    const float* gp = roi_base + (roi_rel + ry0 * roi.z + rx);     // only dereferenced under gmask
-    asm volatile("" : "+l"(gp));    // keep the finished 64-bit pointer: otherwise base + offset is re-derived for every load (6 instr.)
-    const int gw2 = 2 * roi.z;
+    unsigned gmask = 0u;                                           // bit pass: the lane's ROW of that pass lies in the patch
+    if (phi > plo) gmask = ((1u << (phi - plo)) - 1u) << plo;
+    // GT = col[row in patch] * row[column in patch]  (one fp32 product: the definition of the factored heatmap, heatmaps.py)
+    const float grow = ((unsigned)rx < (unsigned)roi.z) ? __ldg(fp + roi.w + rx) : 0.f;      // 0 outside the patch's columns => GT 0
+    const float* gp = fp + ry0;                                    // column profile at the lane's row of pass 0; only dereferenced under gmask
+    asm volatile("" : "+l"(gp));    // keep the finished 64-bit pointer: otherwise base + offset is re-derived for every load
     float acc[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (lx < W) {
         const float dx = __fsub_rn(A.x, (float)lx);
@@ -345,7 +348,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
 #pragma unroll
             for (int q = 0; q < PP; q++) {
                 gtv[q] = 0.f;
-                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = SSB_GT_LOAD(gp + (pass0 + q) * gw2);
+                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = SSB_GT_COL(gp + 2 * (pass0 + q)) * grow;
             }
 #pragma unroll
             for (int q = 0; q < PP; q++) {
@@ -375,7 +378,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
 // recurrence reduces to S = alpha1 * err1 for Gaussian 0.  Per-entry constants live in registers for the whole tile.
 // Bit-identical to tile_fast<2, 1>.
 __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* __restrict__ list, const int4* __restrict__ roi_v,
-                                         const int* __restrict__ roi_rel_v, const float* __restrict__ roi_base,
+                                         const float* const* __restrict__ fac_v,
                                          int lx, int ly0, int W, int H, float* __restrict__ part_out, int lane)
 {
     const int ty0 = ly0 - (lane >> 4);                             // tile origin row (warp-uniform)
@@ -388,8 +391,8 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
     }
     vhi = min(vhi, (H - 1 - ty0) >> 1);
     const float* gptr[2];
-    int gw2[2];
-    unsigned gmask = 0u;                                           // bit (8u + pass): the lane's pixel of that pass lies in patch u
+    float grow[2];
+    unsigned gmask = 0u;                                           // bit (8u + pass): the lane's ROW of that pass lies in patch u
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         const int g = u ? g1 : g0;
@@ -398,10 +401,11 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
         int plo = ry0 < 0 ? ((1 - ry0) >> 1) : 0;
         int phi = (roi.w - ry0 + 1) >> 1;
         phi = phi > TILE / 2 ? TILE / 2 : phi;
-        if ((unsigned)rx < (unsigned)roi.z && phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
-        gptr[u] = roi_base + (roi_rel_v[g] + ry0 * roi.z + rx);
+        if (phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
+        const float* fp = fac_v[g];
+        grow[u] = ((unsigned)rx < (unsigned)roi.z) ? __ldg(fp + roi.w + rx) : 0.f;
+        gptr[u] = fp + ry0;
         asm volatile("" : "+l"(gptr[u]));
-        gw2[u] = 2 * roi.z;
     }
     float acc0[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc1[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (lx < W) {
@@ -412,8 +416,8 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
         for (int pass = vlo; pass <= vhi; pass++) {
             const unsigned gm = gmask >> pass;
             float gt0 = 0.f, gt1 = 0.f;
-            if (gm & 1u) gt0 = SSB_GT_LOAD(gptr[0] + pass * gw2[0]);
-            if (gm & 0x100u) gt1 = SSB_GT_LOAD(gptr[1] + pass * gw2[1]);
+            if (gm & 1u) gt0 = SSB_GT_COL(gptr[0] + 2 * pass) * grow[0];
+            if (gm & 0x100u) gt1 = SSB_GT_COL(gptr[1] + 2 * pass) * grow[1];
             const int py = ly0 + 2 * pass;
             if (py < H) {
                 const float pyf = (float)py;
@@ -462,8 +466,11 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     __shared__ float s_halfW[MAXV], s_halfH[MAXV];
     __shared__ float s_tfx[MAXV], s_tfy[MAXV], s_fx[MAXV], s_fy[MAXV];
     __shared__ int4 s_roi[MAXV][MAXJ];          // x0, y0, w, h
-    __shared__ int s_roi_rel[MAXV][MAXJ];        // float offset relative to the frame's first patch
+    __shared__ int s_roi_rel[MAXV][MAXJ];        // float offset of the patch's profiles (col[h] | row[w]) relative to the frame's first patch
     __shared__ long long s_roi_base;
+    __shared__ const float* s_fac[MAXV][MAXJ];   // per (view, joint): the patch's profiles col[h] | row[w] in global memory (finished pointers).
+                                                 // Staging them in shared memory was built and measured: 1.5 % SLOWER than reading them through
+                                                 // L1 (a frame's profiles are ~25 KB and re-read 500 times), bit-identical results -- dropped
     __shared__ int s_ngt[MAXV];            // sum_j #{gt > 0}
     __shared__ float s_sgt2[MAXV];         // sum_j sum gt^2
     __shared__ SlotSplats s_sp[SLOTS];
@@ -502,6 +509,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
         const size_t o = ((size_t)frame * V + v) * J + j;
         s_roi[v][j] = make_int4(p.roi_rect[4 * o], p.roi_rect[4 * o + 1], p.roi_rect[4 * o + 2], p.roi_rect[4 * o + 3]);
         s_roi_rel[v][j] = (int)(p.roi_offset[o] - p.roi_offset[(size_t)frame * V * J]);   // patches of a frame are packed together
+        s_fac[v][j] = p.roi_data + p.roi_offset[o];
     }
     if (tid == 0) s_roi_base = p.roi_offset[(size_t)frame * V * J];
     if (tid == 0) s_status = 0;
@@ -510,9 +518,13 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
     for (int v = 0; v < V; v++) {
         int cnt = 0; float sq = 0.f;
         for (int j = 0; j < J; j++) {
-            const int n = s_roi[v][j].z * s_roi[v][j].w;
-            const float* d = p.roi_data + s_roi_base + s_roi_rel[v][j];
-            for (int i = tid; i < n; i += NT) { const float g = __ldg(d + i); if (g > 0.f) { cnt++; sq = fmaf(g, g, sq); } }
+            const int w = s_roi[v][j].z, h = s_roi[v][j].w, n = w * h;
+            const float* d = p.roi_data + s_roi_base + s_roi_rel[v][j];       // col[h] | row[w]
+            for (int i = tid; i < n; i += NT) {
+                const int a = i / w, b = i - a * w;
+                const float g = __fmul_rn(__ldg(d + a), __ldg(d + h + b));      // the heatmap value: one fp32 product
+                if (g > 0.f) { cnt++; sq = fmaf(g, g, sq); }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); }
@@ -524,7 +536,6 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 
     const int acc = p.cfg.accumulation_steps;     // == SLOTS (host guarantees)
     float last_loss = 0.f;
-
 #if SSB_PHASE_TIMING
     long long t_phase = clock64();
 #endif
@@ -675,7 +686,6 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 #pragma unroll 1
         for (int half = 0; half < HALVES; half++) {
         {
-            const float* roi_base = p.roi_data + s_roi_base;
             const bool unroll5 = p.cfg.max_unrolled_list != 4;          // 0 (default) or 5: lists of five take tile_fast<5>
             // one counter per slot; a warp starts on slot (warp mod SLOTS) and moves on when that slot's tiles are handed out,
             // so everything that depends on the slot only (view, image size, splat table) is loaded once per slot, not per tile
@@ -700,9 +710,9 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 #endif
                 const int lx = (tile & 255) * TILE + (lane & 15), ly0 = (tile >> 8) * TILE + (lane >> 4);
                 float* part_out = d_part + ((size_t)(k - half * RSLOTS) * RCAP + e0) * PSTRIDE;
-#define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
-                if (n == 1) { const int g1 = list[0]; tile_one<SSB_PP_N1>(sp, g1, s_roi[v][g1], s_roi_rel[v][g1], roi_base, lx, ly0, W, H, part_out, lane); }
-                else if (n == 2) tile_two(sp, list, s_roi[v], s_roi_rel[v], roi_base, lx, ly0, W, H, part_out, lane);
+#define SSB_TILE_FAST(NN, PPP) tile_fast<NN, PPP>(sp, list, s_roi[v], s_fac[v], lx, ly0, W, H, part_out, lane);
+                if (n == 1) { const int g1 = list[0]; tile_one<SSB_PP_N1>(sp, g1, s_roi[v][g1], s_fac[v][g1], lx, ly0, W, H, part_out, lane); }
+                else if (n == 2) tile_two(sp, list, s_roi[v], s_fac[v], lx, ly0, W, H, part_out, lane);
                 else if (n == 3 && SSB_FAST_MAX >= 3) SSB_TILE_FAST(3, 1)
                 else if (n == 4 && SSB_FAST_MAX >= 4) SSB_TILE_FAST(4, 1)
                 else if (n == 5 && SSB_FAST_MAX >= 5 && unroll5) SSB_TILE_FAST(5, 1)
@@ -745,7 +755,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                 const int rx = px - roi.x, ry = py - roi.y;
                                 float gt = 0.f;
                                 if ((unsigned)rx < (unsigned)roi.z && (unsigned)ry < (unsigned)roi.w)
-                                    gt = __ldg(roi_base + s_roi_rel[v][g] + ry * roi.z + rx);
+                                    gt = __fmul_rn(__ldg(s_fac[v][g] + ry), __ldg(s_fac[v][g] + roi.w + rx));
                                 const float err = fmaf(alpha, T, -gt);
                                 S = fmaf(last_alpha, last_g - S, S);
                                 last_g = err; last_alpha = alpha;
@@ -906,6 +916,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
 static size_t opt_dyn_smem(int slots, int rcap, int halves) {
     return (size_t)(slots / halves) * rcap * (4 * PSTRIDE) + (size_t)slots * rcap * (2 * 4);
 }
+constexpr int OPT_STATIC_SMEM = 19 * 1024;       // static shared memory (17.0 KB) + the 1 KB the driver reserves per CTA, rounded up
 
 }  // namespace ssb
 
@@ -976,7 +987,7 @@ static int optimize_frames_impl(const ssb_opt_config* cfg, int n_frames, const s
     // two 512-thread CTAs with the records of two slots at a time (HALVES = 2) -- keeps two CTAs up to r_capacity 1024, but
     // measured 4 % SLOWER than the single 1024-thread CTA on the Panoptic shape (5 550 vs 5 784 frames/s, bit-identical
     // results; profiles/README.md) and 2-7 % slower where both fit, so it is only taken on request (resident_record_slots).
-    auto fits2 = [&](int halves) { return SSB_OPT_MIN_CTAS * (opt_dyn_smem(slots, cfg->r_capacity, halves) + 17 * 1024) <= 227 * 1024; };
+    auto fits2 = [&](int halves) { return SSB_OPT_MIN_CTAS * (opt_dyn_smem(slots, cfg->r_capacity, halves) + OPT_STATIC_SMEM) <= 227 * 1024; };
     if (cfg->resident_record_slots != 0 && cfg->resident_record_slots != slots && !(slots == 4 && cfg->resident_record_slots == 2)) return SSB_ERR_INVALID;
     const int halves = cfg->resident_record_slots ? slots / cfg->resident_record_slots : 1;
     const bool big = !fits2(halves);

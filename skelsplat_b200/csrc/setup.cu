@@ -155,7 +155,7 @@ __global__ void roi_rect_kernel(RoiParams p, int* __restrict__ roi_rect, float* 
     roi_rect[4 * (size_t)i] = x0; roi_rect[4 * (size_t)i + 1] = y0; roi_rect[4 * (size_t)i + 2] = x1 - x0 + 1; roi_rect[4 * (size_t)i + 3] = y1 - y0 + 1;
     roi_sigma[2 * (size_t)i] = s1; roi_sigma[2 * (size_t)i + 1] = s2;
     roi_center[2 * (size_t)i] = xc; roi_center[2 * (size_t)i + 1] = yc;
-    roi_size[i] = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
+    roi_size[i] = (long long)(x1 - x0 + 1) + (y1 - y0 + 1);      // factored storage: col[h] | row[w]
 }
 
 // Response at index idx of scipy's correlate1d(mode='reflect') with the truncated Gaussian (sigma, radius) to a unit delta
@@ -172,14 +172,22 @@ __device__ double reflect_response(int idx, int pos, int n, double sigma, int ra
     return acc;
 }
 
-// One CTA per (frame, view, joint) patch: separable filter response, fp32 storage after pass 1 (as scipy does),
-// then per-channel min-max normalisation (min == 0: the patch never covers the whole image) with the +1e-8.
-__global__ void __launch_bounds__(128)
+// FACTORED patches.  Inside its window the heatmap is the product of a column profile and a row profile (a separable filter
+// applied to a delta, then one scalar normalisation), so a patch is stored as h + w floats  col[h] | row[w]  and the heatmap
+// value at window pixel (a, b) is DEFINED as the single fp32 product col[a] * row[b]  (skelsplat_b200/heatmaps.py: same
+// definition; it differs from fl32(fl32(col*row) / denom) by <= ~1.5 ulp).  The fused optimiser keeps the profiles of a frame
+// in shared memory (~25 KB instead of ~410 KB of patches per frame in HBM).
+// One warp per (frame, view, joint) patch: col[a] = fl32(255 * response_y(a)) (scipy stores pass 1 in fp32),
+// row[b] = fl32(response_x(b) / (max col * max response_x + 1e-8)) -- per-channel min-max normalisation with min == 0
+// (the window never covers the whole image).
+constexpr int ROI_WARPS = 4;
+__global__ void __launch_bounds__(ROI_WARPS * 32)
 roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __restrict__ roi_sigma, const int* __restrict__ roi_center,
                 const long long* __restrict__ roi_offset, ssb_cameras cams, int V, int J, float* __restrict__ roi_data,
                 long long capacity, int* __restrict__ status)
 {
-    const int i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * ROI_WARPS + warp;
     if (i >= n_patches) return;
     const int v = (i / J) % V;
     const int W = cams.dims ? cams.dims[2 * v] : cams.W0, H = cams.dims ? cams.dims[2 * v + 1] : cams.H0;
@@ -187,48 +195,45 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
     const double s1 = (double)roi_sigma[2 * (size_t)i], s2 = (double)roi_sigma[2 * (size_t)i + 1];
     const int xc = roi_center[2 * (size_t)i], yc = roi_center[2 * (size_t)i + 1];
     const int ry = (int)(4.0 * s1 + 0.5), rx = (int)(4.0 * s2 + 0.5);
-    __shared__ float s_col[256];
-    __shared__ double s_row[256];
-    __shared__ float s_max;
+    __shared__ double s_term[ROI_WARPS][2][2 * 128 + 1];
+    __shared__ double s_rowd[ROI_WARPS][256];
     if (w > 256 || h > 256 || rx > 128 || ry > 128) {      // sigma > 31 px: not a SkelSplat regime
-        if (status && threadIdx.x == 0) atomicOr(status, (int)SSB_STATUS_ROI_TOO_WIDE);
+        if (status && lane == 0) atomicOr(status, (int)SSB_STATUS_ROI_TOO_WIDE);
         return;
     }
-    if (capacity >= 0 && roi_offset[i] + (long long)w * h > capacity) {       // packed buffer too small: nothing is written
-        if (status && threadIdx.x == 0) atomicOr(status, (int)SSB_STATUS_ROI_OVERFLOW);
+    if (capacity >= 0 && roi_offset[i] + (long long)(w + h) > capacity) {       // packed buffer too small: nothing is written
+        if (status && lane == 0) atomicOr(status, (int)SSB_STATUS_ROI_OVERFLOW);
         return;
     }
-    // normalisation sums of the two truncated kernels: one term per thread, then summed by ONE thread in the sequential
-    // order k = -r..r (the order scipy's / the host generator's loop uses), so the value does not depend on the block shape
-    __shared__ double s_term[2][2 * 128 + 1];
-    __shared__ double s_wsum[2];
-    for (int k = threadIdx.x; k <= 2 * ry; k += blockDim.x) s_term[0][k] = exp(-0.5 / (s1 * s1) * (double)((k - ry) * (k - ry)));
-    for (int k = threadIdx.x; k <= 2 * rx; k += blockDim.x) s_term[1][k] = exp(-0.5 / (s2 * s2) * (double)((k - rx) * (k - rx)));
-    __syncthreads();
-    if (threadIdx.x == 0 || threadIdx.x == 32) {
-        const int a = threadIdx.x ? 1 : 0, r = a ? rx : ry;
-        double acc = 0.0;
-        for (int k = 0; k <= 2 * r; k++) acc += s_term[a][k];
-        s_wsum[a] = acc;
+    // normalisation sums of the two truncated kernels: one term per lane, then summed by ONE lane in the sequential order
+    // k = -r..r (the order scipy's / the host generator's loop uses), so the value does not depend on the launch shape
+    for (int k = lane; k <= 2 * ry; k += 32) s_term[warp][0][k] = exp(-0.5 / (s1 * s1) * (double)((k - ry) * (k - ry)));
+    for (int k = lane; k <= 2 * rx; k += 32) s_term[warp][1][k] = exp(-0.5 / (s2 * s2) * (double)((k - rx) * (k - rx)));
+    __syncwarp();
+    double wsum = 0.0;
+    if (lane < 2) {
+        const int r = lane ? rx : ry;
+        for (int k = 0; k <= 2 * r; k++) wsum += s_term[warp][lane][k];
     }
-    __syncthreads();
-    const double wy = s_wsum[0], wx = s_wsum[1];
-    for (int t = threadIdx.x; t < h; t += blockDim.x) s_col[t] = (float)(255.0 * reflect_response(y0 + t, yc, H, s1, ry, 1.0 / wy));
-    for (int t = threadIdx.x; t < w; t += blockDim.x) s_row[t] = reflect_response(x0 + t, xc, W, s2, rx, 1.0 / wx);
-    __syncthreads();
-    if (threadIdx.x == 0) {      // max of the rounded products == rounded product of the maxima (all factors >= 0, rounding is monotonic)
-        float mc = 0.f; double mr = 0.0;
-        for (int a = 0; a < h; a++) mc = fmaxf(mc, s_col[a]);
-        for (int b = 0; b < w; b++) mr = fmax(mr, s_row[b]);
-        s_max = (float)((double)mc * mr);
-    }
-    __syncthreads();
+    const double wy = __shfl_sync(0xFFFFFFFFu, wsum, 0), wx = __shfl_sync(0xFFFFFFFFu, wsum, 1);
     float* dst = roi_data + roi_offset[i];
-    const float denom = s_max + 1e-8f;
-    for (int t = threadIdx.x; t < w * h; t += blockDim.x) {
-        const int a = t / w, b = t - a * w;
-        dst[t] = (float)((double)s_col[a] * s_row[b]) / denom;
+    float mc = 0.f; double mr = 0.0;
+    for (int t = lane; t < h; t += 32) {
+        const float c = (float)(255.0 * reflect_response(y0 + t, yc, H, s1, ry, 1.0 / wy));
+        dst[t] = c;
+        mc = fmaxf(mc, c);
     }
+    for (int t = lane; t < w; t += 32) {
+        const double r = reflect_response(x0 + t, xc, W, s2, rx, 1.0 / wx);
+        s_rowd[warp][t] = r;
+        mr = fmax(mr, r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mc = fmaxf(mc, __shfl_xor_sync(0xFFFFFFFFu, mc, o)); mr = fmax(mr, __shfl_xor_sync(0xFFFFFFFFu, mr, o)); }
+    // max of the rounded products == rounded product of the maxima (all factors >= 0, rounding is monotonic)
+    const float denom = (float)((double)mc * mr) + 1e-8f;
+    __syncwarp();
+    for (int t = lane; t < w; t += 32) dst[h + t] = (float)(s_rowd[warp][t] / (double)denom);
 }
 
 // Exclusive scan of the patch sizes into packed offsets (+ the total), one CTA of 32 warps: warp w owns the contiguous
@@ -313,7 +318,7 @@ int ssb_heatmap_roi_fill(int n_frames, int J, const ssb_cameras* cams, const int
     if (n_frames == 0) return SSB_OK;
     if (!roi_rect || !roi_sigma || !roi_center || !roi_offset || !roi_data) return SSB_ERR_INVALID;
     const int n = n_frames * cams->n_views * J;
-    roi_fill_kernel<<<n, 128, 0, (cudaStream_t)stream_>>>(n, roi_rect, roi_sigma, roi_center, (const long long*)roi_offset, *cams,
+    roi_fill_kernel<<<(n + ROI_WARPS - 1) / ROI_WARPS, ROI_WARPS * 32, 0, (cudaStream_t)stream_>>>(n, roi_rect, roi_sigma, roi_center, (const long long*)roi_offset, *cams,
                                                           cams->n_views, J, roi_data, (long long)capacity, status);
     return ssb_set_cuda_error(cudaGetLastError());
 }

@@ -141,30 +141,32 @@ ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restr
                     issue_row(i + SS_NB - 1);                          // (an empty group past the last row keeps the count uniform)
                     const float2* buf = mybuf + (i & (SS_NB - 1)) * SS_BUFW;
                     // horizontal pass: 11 taps, (u,v) pairs straight from shared memory
-                    f32x2 hm = 0ull, he = 0ull;
-                    float hx = 0.f;
+                    // (two partial sums per moment -- even / odd taps -- halve the dependent-FMA chains: the kernel is bound by
+                    // FMA latency x issue, not by memory)
+                    f32x2 hm = 0ull, he = 0ull, hm1 = 0ull, he1 = 0ull;
+                    float hx = 0.f, hx1 = 0.f;
 #pragma unroll
                     for (int k = 0; k < 11; k++) {
                         const float2 uv = buf[k];
                         const f32x2 p = pack2(uv.x, uv.y);
                         const f32x2 g2 = gg[k <= 5 ? k : 10 - k];
-                        hm = fma2(g2, p, hm);
-                        he = fma2(g2, mul2(p, p), he);
-                        hx = fmaf(ss_g(k), uv.x * uv.y, hx);
+                        if (k & 1) { hm1 = fma2(g2, p, hm1); he1 = fma2(g2, mul2(p, p), he1); hx1 = fmaf(ss_g(k), uv.x * uv.y, hx1); }
+                        else { hm = fma2(g2, p, hm); he = fma2(g2, mul2(p, p), he); hx = fmaf(ss_g(k), uv.x * uv.y, hx); }
                     }
-                    ring_m[ii] = hm; ring_e[ii] = he; ring_x[ii] = hx;
+                    const f32x2 one2 = pack2(1.0f, 1.0f);
+                    ring_m[ii] = fma2(hm1, one2, hm); ring_e[ii] = fma2(he1, one2, he); ring_x[ii] = hx + hx1;
                     if (i >= 2 * SS_R) {
                         // vertical pass over the register ring: the oldest row sits at (ii + 1) % 11
-                        f32x2 vm = 0ull, ve = 0ull;
-                        float e12 = 0.f;
+                        f32x2 vm = 0ull, ve = 0ull, vm1 = 0ull, ve1 = 0ull;
+                        float e12 = 0.f, e12b = 0.f;
 #pragma unroll
                         for (int k = 0; k < 11; k++) {
                             const int r = (ii + 1 + k) % 11;
                             const f32x2 g2 = gg[k <= 5 ? k : 10 - k];
-                            vm = fma2(g2, ring_m[r], vm);
-                            ve = fma2(g2, ring_e[r], ve);
-                            e12 = fmaf(ss_g(k), ring_x[r], e12);
+                            if (k & 1) { vm1 = fma2(g2, ring_m[r], vm1); ve1 = fma2(g2, ring_e[r], ve1); e12b = fmaf(ss_g(k), ring_x[r], e12b); }
+                            else { vm = fma2(g2, ring_m[r], vm); ve = fma2(g2, ring_e[r], ve); e12 = fmaf(ss_g(k), ring_x[r], e12); }
                         }
+                        vm = fma2(vm1, one2, vm); ve = fma2(ve1, one2, ve); e12 += e12b;
                         if (cw) {
                             float mu1, mu2, e11, e22;
                             unpack2(vm, mu1, mu2); unpack2(ve, e11, e22);
@@ -228,7 +230,9 @@ ssim_mean_finalize_kernel(const float* __restrict__ partials, long long n, doubl
 // zero-filled by the copies and the scalar is applied after the convolutions.
 constexpr int SS_BUFW_B = 44;        // >= 32 + 2*SS_R
 // dynamic shared memory per CTA: per warp a ring of SS_NB input rows (float4) + SS_NB rows of (img1, img2) at the output pixels
-constexpr size_t SS_BWD_SMEM = (size_t)SS_WARPS * SS_NB * (SS_BUFW_B * sizeof(float4) + 32 * sizeof(float2));
+constexpr int SS_BWD_STREAMS = 4;    // dm/dmu1, dm/dsigma1^2, dm/dsigma12, dL/dmap: one float array each (structure of arrays: the 4-byte
+                                     // cp.async writes and the per-tap reads of a warp are then conflict-free)
+constexpr size_t SS_BWD_SMEM = (size_t)SS_WARPS * SS_NB * (SS_BWD_STREAMS * SS_BUFW_B * sizeof(float) + 32 * sizeof(float2));
 template <bool MEAN>
 __global__ void __launch_bounds__(SS_WARPS * 32)
 ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const float* __restrict__ img2,
@@ -237,8 +241,8 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
                 float* __restrict__ dL_dimg1)
 {
     extern __shared__ __align__(16) unsigned char ss_dyn[];
-    float4 (*s_row)[SS_NB][SS_BUFW_B] = reinterpret_cast<float4 (*)[SS_NB][SS_BUFW_B]>(ss_dyn);     // (dm/dmu1, dm/dsigma1^2, dm/dsigma12, dL/dmap)
-    float2 (*s_pix)[SS_NB][32] = reinterpret_cast<float2 (*)[SS_NB][32]>(ss_dyn + (size_t)SS_WARPS * SS_NB * SS_BUFW_B * sizeof(float4));
+    float (*s_row)[SS_NB][SS_BWD_STREAMS][SS_BUFW_B] = reinterpret_cast<float (*)[SS_NB][SS_BWD_STREAMS][SS_BUFW_B]>(ss_dyn);
+    float2 (*s_pix)[SS_NB][32] = reinterpret_cast<float2 (*)[SS_NB][32]>(ss_dyn + (size_t)SS_WARPS * SS_NB * SS_BWD_STREAMS * SS_BUFW_B * sizeof(float));
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SS_KEEP(lane); SS_KEEP(warp);
     const size_t plane = (size_t)blockIdx.z * H * W;
@@ -258,8 +262,9 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
 #define cb (flags & 2)
 #define cw (flags & 4)
 #define lo10 (flags & 8)
-    float4* mybuf = &s_row[warp][0][lane];
+    float* mybuf = &s_row[warp][0][0][lane];
     float2* mypix = &s_pix[warp][0][lane];
+    constexpr int RS = SS_BWD_STREAMS * SS_BUFW_B;      // floats per ring row
     f32x2 gg[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) gg[k] = pack2(ss_g(k), ss_g(k));
@@ -275,14 +280,14 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
         const int y = y0 - SS_R + row;
         const bool yv = y >= crop && y < H - crop && row < n_in;
         const ptrdiff_t base = yv ? (ptrdiff_t)y * W : 0;
-        float4* dst = mybuf + (row & (SS_NB - 1)) * SS_BUFW_B;
+        float* dst = mybuf + (row & (SS_NB - 1)) * RS;
         const bool va_ = yv && ca, vb_ = yv && cb;
         const ptrdiff_t ia = va_ ? base + xa : 0, ib_ = vb_ ? base + xb : 0;
-        cp_async4(&dst->x, q1 + ia, va_); cp_async4(&dst->y, q2 + ia, va_); cp_async4(&dst->z, q3 + ia, va_);
-        if (!MEAN) cp_async4(&dst->w, q0 + ia, va_);
+        cp_async4(dst, q1 + ia, va_); cp_async4(dst + SS_BUFW_B, q2 + ia, va_); cp_async4(dst + 2 * SS_BUFW_B, q3 + ia, va_);
+        if (!MEAN) cp_async4(dst + 3 * SS_BUFW_B, q0 + ia, va_);
         if (lo10) {
-            cp_async4(&dst[32].x, q1 + ib_, vb_); cp_async4(&dst[32].y, q2 + ib_, vb_); cp_async4(&dst[32].z, q3 + ib_, vb_);
-            if (!MEAN) cp_async4(&dst[32].w, q0 + ib_, vb_);
+            cp_async4(dst + 32, q1 + ib_, vb_); cp_async4(dst + SS_BUFW_B + 32, q2 + ib_, vb_); cp_async4(dst + 2 * SS_BUFW_B + 32, q3 + ib_, vb_);
+            if (!MEAN) cp_async4(dst + 3 * SS_BUFW_B + 32, q0 + ib_, vb_);
         }
         const int yo = y0 + row - 2 * SS_R;
         const bool vo = row >= 2 * SS_R && row < n_in && cw;
@@ -305,26 +310,28 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
                 cp_async_wait<SS_NB - 2>();
                 __syncwarp();
                 issue_row(i + SS_NB - 1);
-                const float4* buf = mybuf + (i & (SS_NB - 1)) * SS_BUFW_B;
-                f32x2 hab = 0ull;
-                float hc = 0.f;
+                const float* buf = mybuf + (i & (SS_NB - 1)) * RS;
+                f32x2 hab = 0ull, hab1 = 0ull;
+                float hc = 0.f, hc1 = 0.f;
+                const f32x2 one2 = pack2(1.0f, 1.0f);
 #pragma unroll
                 for (int k = 0; k < 11; k++) {
-                    float4 t = buf[k];
-                    if (!MEAN) { t.x *= t.w; t.y *= t.w; t.z *= t.w; }
-                    hab = fma2(gg[k <= 5 ? k : 10 - k], pack2(t.x, t.y), hab);
-                    hc = fmaf(ss_g(k), t.z, hc);
+                    float ta = buf[k], tb = buf[SS_BUFW_B + k], tc = buf[2 * SS_BUFW_B + k];
+                    if (!MEAN) { const float dl = buf[3 * SS_BUFW_B + k]; ta *= dl; tb *= dl; tc *= dl; }
+                    if (k & 1) { hab1 = fma2(gg[k <= 5 ? k : 10 - k], pack2(ta, tb), hab1); hc1 = fmaf(ss_g(k), tc, hc1); }
+                    else { hab = fma2(gg[k <= 5 ? k : 10 - k], pack2(ta, tb), hab); hc = fmaf(ss_g(k), tc, hc); }
                 }
-                ring_ab[ii] = hab; ring_c[ii] = hc;
+                ring_ab[ii] = fma2(hab1, one2, hab); ring_c[ii] = hc + hc1;
                 if (i >= 2 * SS_R) {
-                    f32x2 vab = 0ull;
-                    float vc = 0.f;
+                    f32x2 vab = 0ull, vab1 = 0ull;
+                    float vc = 0.f, vc1 = 0.f;
 #pragma unroll
                     for (int k = 0; k < 11; k++) {
                         const int r = (ii + 1 + k) % 11;
-                        vab = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[r], vab);
-                        vc = fmaf(ss_g(k), ring_c[r], vc);
+                        if (k & 1) { vab1 = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[r], vab1); vc1 = fmaf(ss_g(k), ring_c[r], vc1); }
+                        else { vab = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[r], vab); vc = fmaf(ss_g(k), ring_c[r], vc); }
                     }
+                    vab = fma2(vab1, one2, vab); vc += vc1;
                     if (cw) {
                         float a, b;
                         unpack2(vab, a, b);

@@ -122,17 +122,24 @@ def _filtered_delta_1d(n, pos, sigma, amplitude, dtype):
 
 @dataclass
 class HeatmapROIs:
-    """Packed ROI patches of one frame.  rect[v,j] = (x0, y0, w, h); the patch of (v,j) is
-    ``data[offset[v,j] : offset[v,j] + w*h]`` row-major; values are the normalised heatmap."""
+    """Packed ROI patches of one frame in FACTORED form.  rect[v,j] = (x0, y0, w, h).  Inside its window the heatmap of
+    (v,j) is the product of a column profile and a row profile (a separable filter applied to a delta, then a scalar
+    normalisation), so a patch is stored as ``h + w`` floats ``data[offset[v,j] : offset[v,j] + h + w]`` = col[h] | row[w]
+    and the heatmap value at window pixel (a, b) is the ONE fp32 product ``col[a] * row[b]`` -- by definition: the dense
+    tensors (``rois_to_dense``), the fused optimiser (csrc/optimizer.cu) and the reference arm all use exactly that value."""
     rect: np.ndarray      # [V,J,4] int32
     offset: np.ndarray    # [V,J]   int64
-    data: np.ndarray      # [total] float32
+    data: np.ndarray      # [total] float32: per patch col[h] | row[w]
     sizes: list           # [(W,H)] per view
 
-    def patch(self, v, j):
+    def factors(self, v, j):
         x0, y0, w, h = self.rect[v, j]
         o = self.offset[v, j]
-        return self.data[o:o + w * h].reshape(h, w)
+        return self.data[o:o + h], self.data[o + h:o + h + w]
+
+    def patch(self, v, j):
+        col, row = self.factors(v, j)
+        return col[:, None] * row[None, :]            # float32 x float32 -> float32: one rounding per pixel
 
 
 def heatmap_roi_rects(xyz_init, poses_2d, cams, scaling_raw, rotation, scaling_modifier=1.0):
@@ -167,13 +174,17 @@ def generate_heatmap_rois(xyz_init, poses_2d, cams, scaling_raw, rotation, scali
             yc = int(np.clip(int(poses_2d[v, j, 1]), 0, H - 1))
             y0, col = _filtered_delta_1d(H, yc, s1[v, j], 255.0, f32)      # pass 1 (axis 0), stored float32
             x0, row = _filtered_delta_1d(W, xc, s2[v, j], 1.0, np.float64)  # pass 2 weights
-            patch = (col.astype(np.float64)[:, None] * row[None, :]).astype(f32)
-            mx, mn = patch.max(), f32(0.0) if patch.size < W * H else patch.min()
-            patch = ((patch - mn) / (mx - mn + f32(1e-8))).astype(f32)
-            rect[v, j] = (x0, y0, patch.shape[1], patch.shape[0])
+            # the filtered image is fl32(col[a] * row[b]); its maximum (rounding is monotonic) and the min-max normalisation
+            # (x - 0) / (max - 0 + 1e-8) of general_utils.py:300-304 (the window never covers the whole image, so min = 0):
+            mx = f32(np.float64(col.max()) * row.max())
+            denom = f32(mx + f32(1e-8))
+            # factored storage: the scalar goes into the row profile; value(a, b) := fl32(col[a] * rown[b]), which differs
+            # from fl32(fl32(col[a] * row[b]) / denom) by at most ~1.5 ulp (the reference's own cupy filter differs by more)
+            rown = (row / np.float64(denom)).astype(f32)
+            rect[v, j] = (x0, y0, rown.shape[0], col.shape[0])
             offset[v, j] = total
-            chunks.append(patch.reshape(-1))
-            total += patch.size
+            chunks.append(col.astype(f32)); chunks.append(rown)
+            total += col.shape[0] + rown.shape[0]
     return HeatmapROIs(rect=rect, offset=offset, data=np.concatenate(chunks), sizes=[(c.image_width, c.image_height) for c in cams])
 
 

@@ -250,7 +250,8 @@ def dense_roi_heatmaps(ps: PackedSequence, frame):
         hm = torch.zeros((cfg.n_joints, int(dims[v, 1]), int(dims[v, 0])), dtype=torch.float32, device=ps.xyz.device)
         for j in range(cfg.n_joints):
             x0, y0, w, h = (int(a) for a in rect[v, j])
-            hm[j, y0:y0 + h, x0:x0 + w] = ps.roi_data[int(off[v, j]):int(off[v, j]) + w * h].reshape(h, w)
+            o = int(off[v, j])      # factored patch: col[h] | row[w]; the heatmap value is their fp32 product (heatmaps.HeatmapROIs)
+            hm[j, y0:y0 + h, x0:x0 + w] = ps.roi_data[o:o + h, None] * ps.roi_data[None, o + h:o + h + w]
         out.append(hm)
     return out
 

@@ -37,15 +37,21 @@ def test_heatmap_rois_match_the_host_generator(name):
     assert np.array_equal(rect, host["roi_rect"])     # integer work: every window identical (fp64 sigma, same operation order)
     assert np.array_equal(off, host["roi_offset"])
     F, V, J = rect.shape[:3]
+    peak = 0.0
     for f in range(F):
         for v in range(V):
             for j in range(J):
                 w, h = rect[f, v, j, 2], rect[f, v, j, 3]
-                a = data[off[f, v, j]:off[f, v, j] + w * h]
-                b = host["roi_data"][host["roi_offset"][f, v, j]:host["roi_offset"][f, v, j] + w * h]
+                o, ho = off[f, v, j], host["roi_offset"][f, v, j]
+                col, row = data[o:o + h], data[o + h:o + h + w]                       # factored patch: col[h] | row[w]
+                hcol, hrow = host["roi_data"][ho:ho + h], host["roi_data"][ho + h:ho + h + w]
+                assert np.abs(col - hcol).max() <= 1e-6 * hcol.max() and np.abs(row - hrow).max() <= 1e-6 * hrow.max()
+                a, b = col[:, None] * row[None, :], hcol[:, None] * hrow[None, :]      # the heatmap values (one fp32 product each)
                 assert np.abs(a - b).max() < 2e-6
-                assert np.array_equal(a > 0, b > 0)              # the loss mask {gt > 0} is the same set
-    assert abs(data.max() - 1.0) < 1e-6 and data.min() >= 0.0
+                assert np.array_equal(a > 0, b > 0) and (a > 0).all()               # the loss mask {gt > 0} is the same set: the window
+                peak = max(peak, float(a.max()))
+    assert abs(peak - 1.0) < 1e-6
+    assert data.min() >= 0.0
 
 
 @pytest.mark.parametrize("name", ["h36m", "h36m-occ", "panoptic", "occlusion-person-8v"])
