@@ -553,6 +553,14 @@ def bench_dropin_and_losses(torch, cfg, seq, dev, hbm_peak):
     optimise_frame_dropin(seq.frames[1], seq.cameras, cfg, device=dev, iterations=100)
     torch.cuda.synchronize()
     out["dropin_loop_frames_per_s"] = round(1.0 / ((time.perf_counter() - t0) * cfg.iterations / 100), 3)
+    # the same loop with the per-view iteration body replayed from CUDA graphs (capture cost included: it is paid per frame)
+    optimise_frame_dropin(seq.frames[0], seq.cameras, cfg, device=dev, iterations=8, cuda_graph=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    optimise_frame_dropin(seq.frames[1], seq.cameras, cfg, device=dev, iterations=cfg.iterations, cuda_graph=True)
+    torch.cuda.synchronize()
+    out["dropin_loop_graphed_frames_per_s"] = round(1.0 / (time.perf_counter() - t0), 3)
+    out["dropin_note"] = ("train.py's per-iteration loop on the drop-in packages (dense images, fused loss kernels, torch Adam), one frame, "
+                          "heatmap setup included; eager: ~100 launches/iteration of host time; graphed: one graph replay per iteration + eager Adam")
 
     def ev(fn, reps=10):
         fn(); torch.cuda.synchronize()

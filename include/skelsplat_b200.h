@@ -165,6 +165,19 @@ int ssb_fused_ssim_backward(int B, int CH, int H, int W, float C1, float C2, con
                             const float* dL_dmap, const float* dm_dmu1, const float* dm_dsigma1_sq,
                             const float* dm_dsigma12, float* dL_dimg1, void* stream);
 
+/* One torch.optim.Adam step (default foreach path, eps as given) for the four parameter tensors of ONE frame, written so that the
+ * launch can be captured in a CUDA graph: the step-dependent host scalars of every step are precomputed into step_table (device,
+ * [n_steps][5] floats: -lr_xyz/bc1, -lr_scaling/bc1, -lr_rotation/bc1, -lr_opacity/bc1, sqrt(bc2) with bc = 1 - beta^step, computed in
+ * fp64 like torch's python floats and rounded to fp32) and the step index lives in *step_counter (device; advanced by the kernel).
+ * The xyz gradient is the mean over the V slots of accumulated_grads [V,J,3] (train.py:215-218); exp_avg / exp_avg_sq are [11 J]
+ * (xyz 3J | scaling 3J | rotation 4J | opacity J); one_minus_beta = fp32(1 - beta) with the subtraction done in fp64, as torch forms
+ * the lerp / addcmul scalars.  Replaces scene/gaussian_model.py:217-218 + train.py:215-222 in the graphed
+ * drop-in loop (skelsplat_b200/training.py:GraphedFrameOptimizer). */
+int ssb_adam_frame_step(int J, int V, float* xyz, float* scaling, float* rotation, float* opacity, const float* accumulated_grads,
+                        const float* g_scaling, const float* g_rotation, const float* g_opacity, float* exp_avg, float* exp_avg_sq,
+                        const float* step_table, int n_steps, int* step_counter, float one_minus_beta1, float beta2, float one_minus_beta2,
+                        float eps, void* stream);
+
 /* The form fused_ssim() actually consumes -- map.mean() (fused_ssim/__init__.py:34-41) -- without materialising the map or
  * dL/dmap: forward writes the mean over the pixels at least `crop` away from the border (0: padding "same"; 5: "valid") to
  * *mean_out (device) and, when the dm_* pointers are given, the three derivative maps; backward takes dL/dmean as a device

@@ -34,3 +34,9 @@ elif what == "ssim":
         fused_ssim(a, b).backward()
         fused_ssim(a.detach(), b, train=False)
     torch.cuda.synchronize()
+elif what == "setup":
+    from skelsplat_b200 import setup_gpu
+    seq, p2d, init, gt = bench.make_detection_batch(cfg, 2048, 0)
+    for _ in range(2):
+        ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, torch.from_numpy(p2d), None, dev)      # DLT + ROI rects / offsets / profiles
+    torch.cuda.synchronize()

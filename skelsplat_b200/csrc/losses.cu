@@ -169,6 +169,46 @@ static int loss_grid(int64_t n) {
     return (int)blocks;
 }
 
+// ------------------------------------------------------------------------------------------ Adam (graph-capturable)
+// One optimiser step for the four parameter tensors of ONE frame, exactly as torch.optim.Adam's default foreach path
+// (scene/gaussian_model.py:217-218, train.py:215-222): exp_avg.lerp_(g, 1 - b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2);
+// denom = sqrt(exp_avg_sq) / sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr / bc1) -- with the step-dependent python-float
+// scalars (fp64 on the host, rounded to fp32 where torch hands them to an fp32 tensor op) precomputed for every step in a
+// device table and the step index read from (and advanced in) device memory, so the launch can be captured in a CUDA graph
+// and replayed: the same arithmetic as phase E of the fused optimiser (optimizer.cu).
+// table: [n_steps][5] = -lr_xyz/bc1, -lr_scaling/bc1, -lr_rotation/bc1, -lr_opacity/bc1, sqrt(bc2).
+// The xyz gradient is the mean over the V view slots of accumulated_grads (stale / zero slots included, train.py:215-218).
+#include "adam_form.h"
+__global__ void adam_frame_kernel(int J, int V, float* __restrict__ xyz, float* __restrict__ scaling, float* __restrict__ rotation,
+                                  float* __restrict__ opacity, const float* __restrict__ accumulated_grads, const float* __restrict__ g_scaling,
+                                  const float* __restrict__ g_rotation, const float* __restrict__ g_opacity, float* __restrict__ exp_avg,
+                                  float* __restrict__ exp_avg_sq, const float* __restrict__ table, int n_steps, int* __restrict__ step_counter,
+                                  float one_minus_beta1, float beta2, float one_minus_beta2, float eps)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = *step_counter;
+    if (i < J * 11 && step < n_steps) {
+        const float* t = table + (size_t)step * 5;
+        float g, neg_step;
+        float* param;
+        if (i < 3 * J) {
+            float a = 0.f;
+            for (int v = 0; v < V; v++) a += accumulated_grads[(size_t)v * J * 3 + i];
+            g = a / (float)V;
+            neg_step = t[0]; param = xyz + i;
+        } else if (i < 6 * J) { g = g_scaling[i - 3 * J]; neg_step = t[1]; param = scaling + (i - 3 * J); }
+        else if (i < 10 * J) { g = g_rotation[i - 6 * J]; neg_step = t[2]; param = rotation + (i - 6 * J); }
+        else { g = g_opacity[i - 10 * J]; neg_step = t[3]; param = opacity + (i - 10 * J); }
+        const float m = fmaf(one_minus_beta1, g - exp_avg[i], exp_avg[i]);
+        const float vv = SSB_ADAM_SECOND_MOMENT(one_minus_beta2, g, exp_avg_sq[i] * beta2);
+        exp_avg[i] = m; exp_avg_sq[i] = vv;
+        const float denom = sqrtf(vv) / t[4] + eps;
+        *param = fmaf(neg_step, m / denom, *param);
+    }
+    __syncthreads();                      // every thread has read the step index (one CTA: J * 11 <= 220 threads)
+    if (i == 0) *step_counter = step + 1;
+}
+
 }  // namespace ssb
 
 using namespace ssb;
@@ -214,6 +254,19 @@ int ssb_limb_consistency(int n_frames, int J, const float* xyz, const int* pairs
         lp.p[i] = pairs_host[i];
     }
     limb_consistency_kernel<<<(n_frames + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(n_frames, J, xyz, lp, loss, grad);
+    return ssb_set_cuda_error(cudaGetLastError());
+}
+
+int ssb_adam_frame_step(int J, int V, float* xyz, float* scaling, float* rotation, float* opacity, const float* accumulated_grads,
+                        const float* g_scaling, const float* g_rotation, const float* g_opacity, float* exp_avg, float* exp_avg_sq,
+                        const float* step_table, int n_steps, int* step_counter, float one_minus_beta1, float beta2, float one_minus_beta2,
+                        float eps, void* stream_) {
+    if (J <= 0 || J * 11 > 1024 || V <= 0 || n_steps <= 0) return SSB_ERR_INVALID;
+    if (!xyz || !scaling || !rotation || !opacity || !accumulated_grads || !g_scaling || !g_rotation || !g_opacity || !exp_avg || !exp_avg_sq ||
+        !step_table || !step_counter) return SSB_ERR_INVALID;
+    adam_frame_kernel<<<1, ((J * 11 + 31) / 32) * 32, 0, (cudaStream_t)stream_>>>(J, V, xyz, scaling, rotation, opacity, accumulated_grads, g_scaling,
+                                                                                 g_rotation, g_opacity, exp_avg, exp_avg_sq, step_table, n_steps,
+                                                                                 step_counter, one_minus_beta1, beta2, one_minus_beta2, eps);
     return ssb_set_cuda_error(cudaGetLastError());
 }
 

@@ -23,9 +23,12 @@
 //     backward recurrence into one scalar recurrence per pixel;
 //   * Adam (torch.optim.Adam semantics, eps=1e-15) runs in-kernel with host-computed fp64 step sizes.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "api_internal.h"
+#include "adam_form.h"
 
 namespace ssb {
 
@@ -60,7 +63,8 @@ __device__ unsigned long long g_list_hist[24];      // tiles by list length (ind
 #ifdef SSB_EXP_NOGT
 #define SSB_GT_COL(p) (0.25f)
 #else
-#define SSB_GT_COL(p) __ldg(p)        // the profiles are ~25 KB per frame and re-read every iteration: they live in L1 / L2
+#define SSB_GT_COL(p) (*(p))          // plain (L1-cached) load: the profiles are ~25 KB per frame and re-read every iteration.  The
+                                      // read-only path (__ldg, LDG.CONSTANT) measured 4 % SLOWER for the whole kernel
 #endif
 #ifdef SSB_EXP_FASTEXP
 #define SSB_EXPF(x) __expf(x)
@@ -92,6 +96,7 @@ struct OptParams {
     float* final_loss; int* status;
     // debug accessor (ssb_optimize_frames_debug; NULL in production): the binning of frame dbg_frame at Adam step dbg_step
     int* dbg; int dbg_frame, dbg_step;
+    float one_minus_beta1, one_minus_beta2;    // fp32(1 - beta) with the subtraction in fp64, as torch forms the scalar (fp32(1 - 0.999) != 1.0f - 0.999f)
 };
 
 // Reduce V (power of two) values across the warp with V-1+log2(32/V) shuffles.  On return every lane
@@ -227,7 +232,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
         phi = phi > TILE / 2 ? TILE / 2 : phi;
         if (phi > plo) gmask |= (mask_t)(((1u << (phi - plo)) - 1u) << plo) << (8 * u);
         const float* fp = fac_v[g];                                // col[h] | row[w]
-        grow[u] = ((unsigned)rx < (unsigned)roi.z) ? __ldg(fp + roi.w + rx) : 0.f;
+        grow[u] = ((unsigned)rx < (unsigned)roi.z) ? fp[roi.w + rx] : 0.f;
         gptr[u] = fp + ry0;
         asm volatile("" : "+l"(gptr[u]));   // keep the finished 64-bit pointer (else base + offset is re-derived per load)
     }
@@ -336,7 +341,7 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
     unsigned gmask = 0u;                                           // bit pass: the lane's ROW of that pass lies in the patch
     if (phi > plo) gmask = ((1u << (phi - plo)) - 1u) << plo;
     // GT = col[row in patch] * row[column in patch]  (one fp32 product: the definition of the factored heatmap, heatmaps.py)
-    const float grow = ((unsigned)rx < (unsigned)roi.z) ? __ldg(fp + roi.w + rx) : 0.f;      // 0 outside the patch's columns => GT 0
+    const float grow = ((unsigned)rx < (unsigned)roi.z) ? fp[roi.w + rx] : 0.f;      // 0 outside the patch's columns => GT 0
     const float* gp = fp + ry0;                                    // column profile at the lane's row of pass 0; only dereferenced under gmask
     asm volatile("" : "+l"(gp));    // keep the finished 64-bit pointer: otherwise base + offset is re-derived for every load
     float acc[PSTRIDE] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -403,7 +408,7 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
         phi = phi > TILE / 2 ? TILE / 2 : phi;
         if (phi > plo) gmask |= (((1u << (phi - plo)) - 1u) << plo) << (8 * u);
         const float* fp = fac_v[g];
-        grow[u] = ((unsigned)rx < (unsigned)roi.z) ? __ldg(fp + roi.w + rx) : 0.f;
+        grow[u] = ((unsigned)rx < (unsigned)roi.z) ? fp[roi.w + rx] : 0.f;
         gptr[u] = fp + ry0;
         asm volatile("" : "+l"(gptr[u]));
     }
@@ -755,7 +760,7 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
                                 const int rx = px - roi.x, ry = py - roi.y;
                                 float gt = 0.f;
                                 if ((unsigned)rx < (unsigned)roi.z && (unsigned)ry < (unsigned)roi.w)
-                                    gt = __fmul_rn(__ldg(s_fac[v][g] + ry), __ldg(s_fac[v][g] + roi.w + rx));
+                                    gt = __fmul_rn(s_fac[v][g][ry], s_fac[v][g][roi.w + rx]);
                                 const float err = fmaf(alpha, T, -gt);
                                 S = fmaf(last_alpha, last_g - S, S);
                                 last_g = err; last_alpha = alpha;
@@ -895,8 +900,8 @@ optimize_kernel(const __grid_constant__ OptParams p, const __grid_constant__ Ste
             } else if (i < 6 * J) { g = s_grad[i]; neg_step = tab.neg_step_scaling[step]; param = &s_scal[i - 3 * J]; }
             else if (i < 10 * J) { g = s_grad[i]; neg_step = tab.neg_step_rotation[step]; param = &s_rot[i - 6 * J]; }
             else { g = s_grad[i]; neg_step = tab.neg_step_opacity[step]; param = &s_opa[i - 10 * J]; }
-            const float m = fmaf(1.0f - p.cfg.beta1, g - s_m[i], s_m[i]);                 // lerp_(grad, 1-beta1)
-            const float vv = fmaf((1.0f - p.cfg.beta2) * g, g, s_v[i] * p.cfg.beta2);    // mul_(beta2).addcmul_(g, g, 1-beta2)
+            const float m = fmaf(p.one_minus_beta1, g - s_m[i], s_m[i]);                  // lerp_(grad, 1-beta1)
+            const float vv = SSB_ADAM_SECOND_MOMENT(p.one_minus_beta2, g, s_v[i] * p.cfg.beta2);   // mul_(beta2).addcmul_(g, g, 1-beta2)
             s_m[i] = m; s_v[i] = vv;
             const float denom = sqrtf(vv) / tab.bc2_sqrt[step] + p.cfg.eps;
             *param = fmaf(neg_step, m / denom, *param);                                   // addcdiv_(m, denom, -step_size)
@@ -961,17 +966,22 @@ static int optimize_frames_impl(const ssb_opt_config* cfg, int n_frames, const s
     if (!xyz || !scaling_raw || !rotation_raw || !opacity_raw || !roi_rect || !roi_offset || !roi_data || !workspace) return SSB_ERR_INVALID;
 
     // Host scalars exactly as torch.optim.Adam's foreach path computes them (python floats = fp64),
-    // then rounded to fp32 where torch hands them to an fp32 tensor op.
+    // then rounded to fp32 where torch hands them to an fp32 tensor op.  The config carries betas and learning rates as fp32;
+    // torch sees the decimal literal of the yaml as a python float (0.9, not 0.9f = 0.89999998), so each is taken back to the
+    // shortest decimal that round-trips the fp32 value before it enters the fp64 arithmetic.
+    auto as_written = [](float x) { char buf[32]; std::snprintf(buf, sizeof(buf), "%.7g", (double)x); return std::strtod(buf, nullptr); };
+    const double b1 = as_written(cfg->beta1), b2 = as_written(cfg->beta2);
+    const double lr_s = as_written(cfg->lr_scaling), lr_r = as_written(cfg->lr_rotation), lr_o = as_written(cfg->lr_opacity);
     StepTable tab;
     for (int s = 0; s < n_steps; s++) {
         const double step = (double)(s + 1);
-        const double bc1 = 1.0 - std::pow((double)cfg->beta1, step);
-        const double bc2 = 1.0 - std::pow((double)cfg->beta2, step);
+        const double bc1 = 1.0 - std::pow(b1, step);
+        const double bc2 = 1.0 - std::pow(b2, step);
         const int it = (s + 1) * cfg->accumulation_steps;          // lr is taken at the stepping iteration
         tab.neg_step_xyz[s] = (float)(-(lr_xyz_host[it] / bc1));
-        tab.neg_step_scaling[s] = (float)(-((double)cfg->lr_scaling / bc1));
-        tab.neg_step_rotation[s] = (float)(-((double)cfg->lr_rotation / bc1));
-        tab.neg_step_opacity[s] = (float)(-((double)cfg->lr_opacity / bc1));
+        tab.neg_step_scaling[s] = (float)(-(lr_s / bc1));
+        tab.neg_step_rotation[s] = (float)(-(lr_r / bc1));
+        tab.neg_step_opacity[s] = (float)(-(lr_o / bc1));
         tab.bc2_sqrt[s] = (float)std::sqrt(bc2);
     }
     OptParams p;
@@ -980,6 +990,7 @@ static int optimize_frames_impl(const ssb_opt_config* cfg, int n_frames, const s
     p.roi_rect = roi_rect; p.roi_offset = roi_offset; p.roi_data = roi_data; p.final_loss = final_loss;
     p.status = (int*)workspace;
     p.dbg = dbg_out; p.dbg_frame = dbg_frame; p.dbg_step = dbg_step;
+    p.one_minus_beta1 = (float)(1.0 - b1); p.one_minus_beta2 = (float)(1.0 - b2);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int slots = cfg->accumulation_steps;
     // Launch shape.  Two 512-thread CTAs per SM when their shared memory fits (227 KB/SM; static + 1 KB reserved per CTA =

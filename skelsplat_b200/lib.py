@@ -49,7 +49,7 @@ EXPORTS = [
     "ssb_version", "ssb_source_hash", "ssb_struct_size", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
     "ssb_state_bytes", "ssb_rasterize_forward", "ssb_backward_scratch_bytes", "ssb_rasterize_backward",
     "ssb_mark_visible", "ssb_state_field_offset",
-    "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency",
+    "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency", "ssb_adam_frame_step",
     "ssb_fused_ssim_forward", "ssb_fused_ssim_backward",
     "ssb_fused_ssim_mean_workspace_bytes", "ssb_fused_ssim_mean_forward", "ssb_fused_ssim_mean_backward",
     "ssb_optimize_workspace_bytes", "ssb_optimize_frames", "ssb_optimize_frames_debug",

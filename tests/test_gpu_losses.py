@@ -113,3 +113,45 @@ def test_fused_ssim_mean_path_equals_the_map_path(shape, padding):
     assert (x.grad - y.grad).abs().max() <= 1e-6 * y.grad.abs().max() + 1e-12
     with pytest.raises(RuntimeError, match="train=True"):
         FS.fused_ssim(a.clone().requires_grad_(True), b, padding, train=False).backward()
+
+
+def test_adam_kernel_is_bit_exact_against_torch_adam():
+    """ssb_adam_frame_step (and phase E of the fused optimiser, which is the same expression) against torch.optim.Adam's own CUDA
+    foreach path with the reference's groups / eps (scene/gaussian_model.py:208-218): 125 steps on random gradients incl. zeros
+    and noise-level values (what eps = 1e-15 amplifies), xyz learning rate changing every step -- every parameter BIT-equal."""
+    import ctypes as C
+    from skelsplat_b200 import lib as L_, configs, training, trainer
+    cfg = configs.PANOPTIC               # opacity lr != 0
+    J, V, n_steps = cfg.n_joints, 4, 125
+    g = torch.Generator().manual_seed(5)
+    P = [torch.randn(J, 3, generator=g) * 500, torch.full((J, 3), 3.0), torch.randn(J, 4, generator=g), torch.randn(J, 1, generator=g)]
+    ref = [torch.nn.Parameter(p.clone().to(DEV)) for p in P]
+    names = ("xyz", "scaling", "rotation", "opacity")
+    ext = 3217.25
+    opt = torch.optim.Adam([{"params": [ref[0]], "lr": cfg.position_lr_init * ext, "name": "xyz"}, {"params": [ref[3]], "lr": cfg.opacity_lr, "name": "opacity"},
+                            {"params": [ref[1]], "lr": cfg.scaling_lr, "name": "scaling"}, {"params": [ref[2]], "lr": cfg.rotation_lr, "name": "rotation"}],
+                           lr=0.0, eps=1e-15)
+    mine = [p.clone().to(DEV) for p in P]
+    table = torch.from_numpy(training.adam_step_table(cfg, ext)).to(DEV)
+    lr = trainer.xyz_lr_table(cfg, ext)
+    exp_avg = torch.zeros(11 * J, device=DEV); exp_avg_sq = torch.zeros(11 * J, device=DEV); counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lib = L_.lib()
+    for s in range(n_steps):
+        acc = torch.randn(V, J, 3, generator=g).to(DEV) * (10.0 ** float(torch.randint(-12, 2, (1,), generator=g)))
+        if s % 7 == 0:
+            acc[1] = 0
+        gs = [torch.randn(J, 3, generator=g).to(DEV) * 1e-3, torch.randn(J, 4, generator=g).to(DEV) * 1e-11, torch.zeros(J, 1, device=DEV)]
+        if s % 5 == 0:
+            gs[2] = torch.randn(J, 1, generator=g).to(DEV) * 1e-6
+        for grp in opt.param_groups:
+            if grp["name"] == "xyz":
+                grp["lr"] = float(lr[(s + 1) * 4])
+        ref[0].grad = acc.mean(dim=0); ref[1].grad, ref[2].grad, ref[3].grad = gs[0].clone(), gs[1].clone(), gs[2].clone()
+        opt.step()
+        p_ = L_.ptr
+        L_.check(lib.ssb_adam_frame_step(C.c_int(J), C.c_int(V), p_(mine[0]), p_(mine[1]), p_(mine[2]), p_(mine[3]), p_(acc), p_(gs[0]), p_(gs[1]), p_(gs[2]),
+                                         p_(exp_avg), p_(exp_avg_sq), p_(table), C.c_int(n_steps), p_(counter), C.c_float(float(np.float32(1 - 0.9))),
+                                         C.c_float(0.999), C.c_float(float(np.float32(1 - 0.999))), C.c_float(1e-15), L_.current_stream()), "adam")
+        for n, a, b in zip(names, mine, ref):
+            assert torch.equal(a, b.detach()), (n, s, float((a - b.detach()).abs().max()))
+    assert int(counter.item()) == n_steps
