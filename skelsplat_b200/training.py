@@ -19,53 +19,6 @@ from .heatmaps import generate_heatmap_rois, rois_to_dense
 from .loss_utils import consistency_losses, losses
 
 
-def _graphed_iterations(gaussians, tcams, heatmaps_dense, render, opt_criterion, consistency_criterion, pipe, bg, poses_2d, cfg,
-                        data_root, accumulated_grads, iterations):
-    """train.py:130-222 with the per-view iteration body replayed from CUDA graphs (one per view; the body of view i is the same
-    launch sequence every time: only the parameter VALUES change, and they live at fixed addresses)."""
-    V = len(tcams)
-    dev = accumulated_grads.device
-    params = [gaussians.get_xyz, gaussians._scaling, gaussians._rotation, gaussians._opacity]
-    static_g = [torch.zeros_like(p) for p in params[1:]]          # scaling / rotation / opacity gradients of the last view rendered
-
-    def body(idx):
-        render_pkg = render(tcams[idx], gaussians, pipe, bg)
-        l2_loss, _ = opt_criterion(render_pkg["render"], heatmaps_dense[idx], poses_2d[idx, :, :2], cfg.lambda_loss_function, reduction="mean")
-        loss = l2_loss + consistency_criterion(gaussians.get_xyz, data_root, reduction="mean") * cfg.lambda_consistency
-        grads = torch.autograd.grad(loss, params)
-        accumulated_grads[idx].copy_(grads[0])
-        for dst, g in zip(static_g, grads[1:]):
-            dst.copy_(g)
-
-    # warm-up on a side stream (allocator / lazy initialisation must not happen during capture); the body does not touch the
-    # parameters, so running it ahead of time changes nothing but gradient buffers that every replay overwrites
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for idx in range(V):
-            body(idx)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    graphs = []
-    for idx in range(V):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            body(idx)
-        graphs.append(g)
-    accumulated_grads.zero_()                                       # train.py:121: the slots start at zero (stale / zero slots matter for V > accumulation_steps)
-    for iteration in range(1, iterations + 1):
-        gaussians.update_learning_rate(iteration)
-        graphs[(iteration - 1) % V].replay()
-        if iteration % cfg.accumulation_steps == 0:
-            gaussians.get_xyz.grad = accumulated_grads.to(gaussians.get_xyz.dtype).mean(dim=0)
-            gaussians._scaling.grad, gaussians._rotation.grad, gaussians._opacity.grad = static_g
-            with torch.no_grad():
-                gaussians.optimizer.step()
-    rendered_ok = torch.isfinite(accumulated_grads).all()
-    if not bool(rendered_ok):           # the overflow watch cannot copy the state header inside a capture: a NaN-filled image shows up here
-        from . import lib as _L
-        raise _L.SkelSplatLibraryError("non-finite gradients in the graphed drop-in loop (rasteriser capacity exceeded? see rasterizer.DEFAULT_R_CAPACITY)")
-
-
 class TorchCamera:
     """Device-tensor view of a cameras.ViewCamera with the attribute names render_* reads (scene/cameras.py)."""
 
@@ -79,13 +32,9 @@ class TorchCamera:
 
 
 def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", iterations=None, modules=None, init_state=None,
-                          return_state=False, spatial_lr_scale=None, cuda_graph=False):
+                          return_state=False, spatial_lr_scale=None):
     """One frame through the drop-in API; returns final xyz [J,3] float32 numpy.
 
-    ``cuda_graph=True``: the iteration body (render -> loss -> autograd.grad -> gradient bookkeeping) is captured once per view in
-    a CUDA graph and replayed; only the learning-rate update and the Adam step (every ``accumulation_steps`` iterations) stay
-    eager.  Same kernels, same order, same results as the eager loop -- the ~100 launches / ~2 ms of host time per iteration
-    become one graph launch (bench.py ``dense_surface.dropin_loop_graphed_frames_per_s``).
     ``frame`` needs ``pose_3d_init`` and ``poses_2d`` (the latter only to build the GT heatmaps when ``heatmaps_dense`` is None).
     ``modules``: optional (GaussianModel, render_functions, losses, consistency_losses) to run the same loop body on another
     implementation of the same surface -- the tests pass the REFERENCE's own classes and functions here (tests/ref_import.py),
@@ -127,12 +76,6 @@ def optimise_frame_dropin(frame, cams, cfg, heatmaps_dense=None, device="cuda", 
     accumulated_grads = torch.zeros((len(tcams),) + tuple(gaussians.get_xyz.shape), device=device)
     # gt_2d argument of the loss table's signature (utils/loss_utils.py:67,86): only the never-configured soft-argmax losses read it
     poses_2d = torch.as_tensor(np.asarray(frame.poses_2d)) if frame.poses_2d is not None else torch.zeros((len(cams), cfg.n_joints, 2))
-    if cuda_graph:
-        if ref_surface:
-            raise ValueError("cuda_graph=True runs on this package's modules (the reference's render_* syncs the host every call)")
-        _graphed_iterations(gaussians, tcams, heatmaps_dense, render, opt_criterion, consistency_criterion, pipe, bg, poses_2d, cfg,
-                            data_root, accumulated_grads, iterations)
-        iterations = 0
     for iteration in range(1, iterations + 1):
         gaussians.update_learning_rate(iteration)
         idx = (iteration - 1) % len(tcams)
