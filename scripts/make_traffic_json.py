@@ -1,10 +1,11 @@
 """Developer tool: profiles/<round>_traffic.json from the ncu captures of gpu_refresh_profiles.sh -- the per-launch DRAM bytes,
 executed instructions and issue-slot utilisation bench.py scales into `roofline.traffic` / `issue_roofline`.  The file records
 the source hash of the library the captures were made with; bench.py ignores it when the loaded library differs.
-usage: make_traffic_json.py [round]   (run in the container: needs `ncu -i`)"""
+usage: make_traffic_json.py [round] [out_dir]   (needs `ncu -i` and the .ncu-rep files under gpurun_out/)"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 R = sys.argv[1] if len(sys.argv) > 1 else "r02"
+OUT_DIR = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
 
 
 def rows(rep):
@@ -39,5 +40,5 @@ if os.path.exists(rep):
     rs = rows(rep)
     out["dense_rasterizer"] = {"views_in_capture": 16, "dram_bytes_read": sum(num(d, "dram__bytes_read.sum") for d in rs),
                                "dram_bytes_write": sum(num(d, "dram__bytes_write.sum") for d in rs), "source": f"profiles/{R}_dense_rasterizer_ncu.txt"}
-json.dump(out, open(os.path.join(ROOT, "profiles", f"{R}_traffic.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(OUT_DIR, f"{R}_traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1)[:1500])

@@ -189,21 +189,25 @@ def test_reference_render_and_losses_on_the_dropin_packages(name):
             assert (ga - gb).abs().max() <= 1e-5 * ga.abs().max() + 1e-30
         if refr.available(variant):
             theirs = ref_import.load("ref")
-            gm = _ref_model(theirs, cfg, fr, cams)
-            with torch.no_grad():
-                gm._scaling.add_(torch.linspace(-0.3, 0.3, gm._scaling.numel(), device=DEV).reshape(gm._scaling.shape))
-                gm._rotation.add_(torch.linspace(-0.2, 0.2, gm._rotation.numel(), device=DEV).reshape(gm._rotation.shape))
-            pkg = theirs.gaussian_renderer.render_functions[cfg.rendering](cam, gm, pipe, bg)
-            l2, _ = theirs.utils.losses["l2_gaussian"](pkg["render"], gt, None, cfg.lambda_loss_function, reduction="mean")
-            loss = l2 + theirs.utils.consistency_losses["3D_length_consistency"](gm.get_xyz, "data/" + cfg.name, reduction="mean") * cfg.lambda_consistency
-            grads = torch.autograd.grad(loss, [gm.get_xyz, gm._scaling, gm._rotation])
+            runs = []
+            for _ in range(2):           # two runs: the reference's backward uses unordered fp32 atomics -- its own spread sets the gradient tolerance
+                gm = _ref_model(theirs, cfg, fr, cams)
+                with torch.no_grad():
+                    gm._scaling.add_(torch.linspace(-0.3, 0.3, gm._scaling.numel(), device=DEV).reshape(gm._scaling.shape))
+                    gm._rotation.add_(torch.linspace(-0.2, 0.2, gm._rotation.numel(), device=DEV).reshape(gm._rotation.shape))
+                pkg = theirs.gaussian_renderer.render_functions[cfg.rendering](cam, gm, pipe, bg)
+                l2, _ = theirs.utils.losses["l2_gaussian"](pkg["render"], gt, None, cfg.lambda_loss_function, reduction="mean")
+                loss = l2 + theirs.utils.consistency_losses["3D_length_consistency"](gm.get_xyz, "data/" + cfg.name, reduction="mean") * cfg.lambda_consistency
+                runs.append([g.detach() for g in torch.autograd.grad(loss, [gm.get_xyz, gm._scaling, gm._rotation])])
+            grads = runs[0]
             assert torch.equal(pkg["radii"], a[0]["radii"])
             ref_img = pkg["render"]
             assert (ref_img - a[0]["render"]).abs().max() <= 1e-5 * ref_img.abs().max()
             assert torch.equal(ref_img > 0, a[0]["render"] > 0)             # the loss mask is the same set of pixels
             assert abs(float(l2) - float(a[1])) <= 1e-5 * abs(float(l2))
-            for gr, ga in zip(grads, a[2]):                                  # the reference's atomics: ~1e-6 relative noise of its own
-                assert (gr - ga).abs().max() <= 2e-5 * gr.abs().max() + 1e-30
+            for gr, gr2, ga in zip(grads, runs[1], a[2]):
+                spread = float((gr - gr2).abs().max() / gr.abs().max())
+                assert float((gr - ga).abs().max() / gr.abs().max()) <= max(2e-5, 4.0 * spread), (name, v, spread)
 
 
 @pytest.mark.gpu
