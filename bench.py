@@ -396,13 +396,15 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    # ncu-derived constants (DRAM traffic, executed instructions) are tied to the build they were captured from: they are
-    # used only when the loaded library's source hash matches the one recorded with them
+    # ncu-derived constants (DRAM traffic, executed instructions) are tied to the kernel they were captured from: they are used
+    # only while the files that define that kernel are the ones the LOADED library was compiled from (ssb_source_manifest)
     traffic = {}
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-        if t.get("source_hash") == L.lib().ssb_source_hash().decode():
-            traffic = t
+        man = L.source_manifest()
+        for kernel, files in t.get("kernel_sources", {}).items():
+            if all(man.get(f) == h for f, h in files.items()):
+                traffic[kernel] = t[kernel]
     except Exception:
         pass
 

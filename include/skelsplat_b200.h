@@ -35,6 +35,8 @@ int         ssb_version(void);              /* 200: + ssb_optimize_frames_debug,
 /* Hex digest of the kernel sources the library was compiled from (skelsplat_b200/build.py passes -DSSB_SOURCE_HASH):
  * a binding compares it with the sources it sits next to and refuses a stale build. */
 const char* ssb_source_hash(void);
+/* "file:hash,file:hash,...": one entry per kernel source / header the library was compiled from. */
+const char* ssb_source_manifest(void);
 int         ssb_struct_size(int which);     /* sizeof: 0 ssb_gaussians, 1 ssb_cameras, 2 ssb_opt_config; -1 otherwise */
 const char* ssb_error_string(int code);
 const char* ssb_last_cuda_error(void);

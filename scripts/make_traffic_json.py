@@ -23,9 +23,13 @@ def num(d, k):
 
 
 from skelsplat_b200 import build
+MAN = dict(e.split(":") for e in build.source_manifest().split(","))
+OPT_FILES = ("optimizer.cu", "common.cuh", "adam_form.h", "api_internal.h", "skelsplat_b200.h")
+DENSE_FILES = ("raster_dense.cu", "common.cuh", "api_internal.h", "skelsplat_b200.h")
 out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum, smsp__issue_active from `ncu --set full` captures "
                    f"(gpurun_out/{R}_*.ncu-rep, summaries in profiles/{R}_*_ncu.txt); bench.py scales them to its launch size and drops them "
-                   "when the loaded library's source hash differs", "source_hash": build.source_hash(), "optimize_kernel": {}}
+                   "when the files that define the captured kernel differ in the loaded library (ssb_source_manifest)",
+       "kernel_sources": {"optimize_kernel": {f: MAN[f] for f in OPT_FILES}, "dense_rasterizer": {f: MAN[f] for f in DENSE_FILES}}, "optimize_kernel": {}}
 for cfg in ("h36m", "h36m-occ", "panoptic", "occlusion-person-8v"):
     rep = os.path.join(ROOT, "gpurun_out", f"{R}_opt_{cfg}.ncu-rep")
     if not os.path.exists(rep):

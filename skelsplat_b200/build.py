@@ -39,6 +39,13 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
+def source_manifest():
+    """"file:hash,file:hash,..." per kernel source / header: compiled into the library (ssb_source_manifest) so that evidence tied
+    to ONE kernel (the ncu constants of profiles/*_traffic.json) can be checked against exactly the files that define it."""
+    import hashlib
+    return ",".join(f"{os.path.basename(d)}:{hashlib.sha256(open(d, 'rb').read()).hexdigest()[:12]}" for d in dependencies())
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True
@@ -52,7 +59,7 @@ def build(force=False, verbose=False, defines=(), out=None):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     out = OUT if out is None else out
-    cmd = [NVCC] + FLAGS + [f'-DSSB_SOURCE_HASH="{source_hash()}"'] + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
+    cmd = [NVCC] + FLAGS + [f'-DSSB_SOURCE_HASH="{source_hash()}"', f'-DSSB_SOURCE_MANIFEST="{source_manifest()}"'] + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

@@ -16,6 +16,10 @@ int ssb_version(void) { return 200; }
 #define SSB_SOURCE_HASH "unknown"
 #endif
 const char* ssb_source_hash(void) { return SSB_SOURCE_HASH; }
+#ifndef SSB_SOURCE_MANIFEST
+#define SSB_SOURCE_MANIFEST ""
+#endif
+const char* ssb_source_manifest(void) { return SSB_SOURCE_MANIFEST; }
 // sizeof of the ABI structs (0: ssb_gaussians, 1: ssb_cameras, 2: ssb_opt_config): lets a binding verify its struct layout
 int ssb_struct_size(int which) {
     switch (which) {

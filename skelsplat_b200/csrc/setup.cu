@@ -158,16 +158,16 @@ __global__ void roi_rect_kernel(RoiParams p, int* __restrict__ roi_rect, float* 
     roi_size[i] = (long long)(x1 - x0 + 1) + (y1 - y0 + 1);      // factored storage: col[h] | row[w]
 }
 
-// Response at index idx of scipy's correlate1d(mode='reflect') with the truncated Gaussian (sigma, radius) to a unit delta
-// at pos on an axis of length n:  sum_k w[k] * [reflect(idx + k - radius) == pos].
-__device__ double reflect_response(int idx, int pos, int n, double sigma, int radius, double wsum_inv) {
+// Response at index idx of scipy's correlate1d(mode='reflect') with the truncated Gaussian (radius taps each side, unnormalised
+// weights term[0 .. 2 radius], 1 / their sum) to a unit delta at pos on an axis of length n:
+//   sum_k w[k] * [reflect(idx + k - radius) == pos].
+__device__ double reflect_response(int idx, int pos, int n, int radius, const double* __restrict__ term, double wsum_inv) {
     double acc = 0.0;
-    const double c = -0.5 / (sigma * sigma);
     for (int k = 0; k <= 2 * radius; k++) {
         int src = idx + k - radius;
         if (src < 0) src = -src - 1;
         if (src >= n) src = 2 * n - 1 - src;
-        if (src == pos) { const double d = (double)(k - radius); acc += exp(c * d * d) * wsum_inv; }
+        if (src == pos) acc += term[k] * wsum_inv;
     }
     return acc;
 }
@@ -219,12 +219,12 @@ roi_fill_kernel(int n_patches, const int* __restrict__ roi_rect, const float* __
     float* dst = roi_data + roi_offset[i];
     float mc = 0.f; double mr = 0.0;
     for (int t = lane; t < h; t += 32) {
-        const float c = (float)(255.0 * reflect_response(y0 + t, yc, H, s1, ry, 1.0 / wy));
+        const float c = (float)(255.0 * reflect_response(y0 + t, yc, H, ry, s_term[warp][0], 1.0 / wy));
         dst[t] = c;
         mc = fmaxf(mc, c);
     }
     for (int t = lane; t < w; t += 32) {
-        const double r = reflect_response(x0 + t, xc, W, s2, rx, 1.0 / wx);
+        const double r = reflect_response(x0 + t, xc, W, rx, s_term[warp][1], 1.0 / wx);
         s_rowd[warp][t] = r;
         mr = fmax(mr, r);
     }

@@ -46,7 +46,7 @@ class OptConfig(C.Structure):
 _lib = None
 
 EXPORTS = [
-    "ssb_version", "ssb_source_hash", "ssb_struct_size", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
+    "ssb_version", "ssb_source_hash", "ssb_source_manifest", "ssb_struct_size", "ssb_error_string", "ssb_last_cuda_error", "ssb_channels_supported",
     "ssb_state_bytes", "ssb_rasterize_forward", "ssb_backward_scratch_bytes", "ssb_rasterize_backward",
     "ssb_mark_visible", "ssb_state_field_offset",
     "ssb_loss_forward", "ssb_loss_backward", "ssb_limb_consistency", "ssb_adam_frame_step",
@@ -75,6 +75,7 @@ def lib():
             raise SkelSplatLibraryError(f"{LIB_PATH} is stale, missing symbols {missing}: rebuild it")
         L.ssb_error_string.restype = C.c_char_p
         L.ssb_source_hash.restype = C.c_char_p
+        L.ssb_source_manifest.restype = C.c_char_p
         if "SKELSPLAT_B200_LIB" not in os.environ:                  # tuning variants are built with other defines on purpose
             from . import build as _b
             if os.path.isdir(_b.CSRC) and _b.sources():
@@ -127,3 +128,9 @@ def state_field_offset(P, W, H, rcap, field):
 
 def backward_scratch_bytes(Cch, rcap):
     return int(lib().ssb_backward_scratch_bytes(C.c_int(Cch), C.c_int(rcap)))
+
+
+def source_manifest():
+    """{file: hash} of the sources the LOADED library was compiled from."""
+    m = lib().ssb_source_manifest().decode()
+    return dict(e.split(":") for e in m.split(",") if ":" in e)

@@ -152,7 +152,7 @@ def default_r_capacity(cfg: SceneConfig):
     """(Gaussian,tile) pairs per view held in shared memory.  ~10/joint at H36M/OP scale, 25-60/joint at Panoptic scale.
     Small capacities raise occupancy; frames that outgrow the capacity are detected on the device and re-run (below)."""
     if cfg.name.startswith("panoptic"):
-        return 1024
+        return 896        # 0 of 4 096 synthetic frames outgrow 768; 896 leaves margin and, vs 1 024, more L1 for the heatmap profiles (+2 %)
     if cfg.name.startswith("occlusion-person"):
         return 512
     return 320        # H36M: 256 is outgrown by ~1 % of the synthetic frames during optimisation; 320 costs 0.5 % throughput
