@@ -36,6 +36,12 @@ if [ "$STAGE" = "ncu" ]; then
   ls -la $P
   rm -f gpurun_out/${R}_*.ncu-rep
 fi
+if [ "$STAGE" = "ncu_setup" ]; then      # re-capture of the setup kernels only (cheap)
+  P=gpurun_out/profiles_${R}
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:roi_|dlt_" -c 4 -o gpurun_out/${R}_setup -f python scripts/profile_target.py setup > gpurun_out/${R}_ncu_setup.log 2>&1
+  python scripts/summarize_ncu.py gpurun_out/${R}_setup.ncu-rep $P/${R}_setup_ncu.txt > /dev/null 2>&1
+  rm -f gpurun_out/${R}_*.ncu-rep
+fi
 if [ "$STAGE" = "sanitize" ]; then
   for tool in memcheck racecheck synccheck; do
     timeout 1200 compute-sanitizer --tool $tool python scripts/gpu_sanitize_target.py 4 > gpurun_out/${R}_sanitize_$tool.log 2>&1; tail -2 gpurun_out/${R}_sanitize_$tool.log
