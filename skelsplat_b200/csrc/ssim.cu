@@ -20,6 +20,7 @@
 // Per-pixel epilogue uses two IEEE reciprocals (1/A, 1/B) instead of the reference's seven divisions; results agree with
 // the reference's kernels to ~1e-6 relative (tests/test_reference_python.py, tests/test_gpu_losses.py).
 #include "api_internal.h"
+#include "f32x2.cuh"
 
 namespace ssb {
 
@@ -40,13 +41,6 @@ __device__ __forceinline__ constexpr float ss_g(int k) {
     return (k == 0 || k == 10) ? SS_G0 : (k == 1 || k == 9) ? SS_G1 : (k == 2 || k == 8) ? SS_G2 : (k == 3 || k == 7) ? SS_G3
          : (k == 4 || k == 6) ? SS_G4 : SS_G5;
 }
-
-// ---- packed fp32 pairs (one 64-bit register pair; FFMA2 / FMUL2 issue ONE instruction for two IEEE fp32 operations)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void unpack2(f32x2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // 1/x for x in [1e-5, 1e4] (the SSIM denominators: >= C1 or ~C2 > 0): approximate reciprocal + one Newton step, <= 1 ulp, no
 // denormal slow path (__frcp_rn compiles to a call with one)
