@@ -29,7 +29,6 @@
 #include "common.cuh"
 #include "api_internal.h"
 #include "adam_form.h"
-#include "f32x2.cuh"
 
 namespace ssb {
 
@@ -45,9 +44,6 @@ constexpr int OPT_THREADS = SSB_OPT_THREADS;
 #endif
 #ifndef SSB_FAST_MAX         // longest tile list with a fully unrolled register-resident tile function compiled in (longer lists:
 #define SSB_FAST_MAX 5       // chunked generic path).  ssb_opt_config::max_unrolled_list selects 4 or 5 at run time (tuning knob).
-#endif
-#ifndef SSB_TILE1_PACKED     // tile_one evaluates its two pixels per trip with packed fp32 math (FFMA2 / FMUL2 / FADD2): same IEEE
-#define SSB_TILE1_PACKED 0   // operations, two per instruction; the two pixels then accumulate into separate partial sums
 #endif
 #ifndef SSB_ROWCULL          // exact row-band culling as warp-uniform pass-loop bounds (0: all 8 passes; bitwise-identical results).
 #define SSB_ROWCULL 1        // An earlier per-(pass, entry) predicate form of the same test measured 8 % SLOWER and was dropped.
@@ -260,7 +256,7 @@ __device__ __forceinline__ void tile_fast(const SlotSplats& sp, const uint16_t* 
 #pragma unroll
                 for (int u = 0; u < N; u++) {
                     gtv[q][u] = 0.f;
-                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = __fmul_rn(SSB_GT_COL(gptr[u] + 2 * (pass0 + q)), grow[u]);
+                    if (gm & ((mask_t)1 << (8 * u + q))) gtv[q][u] = SSB_GT_COL(gptr[u] + 2 * (pass0 + q)) * grow[u];
                 }
             }
             float pyf[PP];
@@ -352,59 +348,12 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
     if (lx < W) {
         const float dx = __fsub_rn(A.x, (float)lx);
         const float dxcx = __fmul_rn(dx, B.x), dxcy = __fmul_rn(dx, B.y);      // pass-invariant factors of pair_alpha's power
-#if SSB_TILE1_PACKED
-        static_assert(PP == 2, "the packed form evaluates exactly two pixels per trip");
-        const f32x2 dx2 = pack2(dx, dx), dxcx2 = pack2(dxcx, dxcx), ndxcy2 = pack2(-dxcy, -dxcy), Bz2 = pack2(B.z, B.z), Ay2 = pack2(A.y, A.y);
-        const f32x2 mhalf2 = pack2(-0.5f, -0.5f);
-        f32x2 a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull, a4 = 0ull, a5 = 0ull, l2 = 0ull;      // (pixel 0, pixel 1) partial sums
-        float cnt = 0.f;
-        for (int pass0 = vlo; pass0 <= vhi; pass0 += 2) {
-            const unsigned gm = gmask >> pass0;
-            float c0 = 0.f, c1 = 0.f;
-            if (gm & 1u) c0 = SSB_GT_COL(gp + 2 * pass0);
-            if (gm & 2u) c1 = SSB_GT_COL(gp + 2 * pass0 + 2);
-            const int py = ly0 + 2 * pass0;
-            const bool live0 = py < H, live1 = (py + 2 < H) && (pass0 + 1 <= vhi);
-            const float pyf = (float)py;
-            // pair_alpha (forward.cu:352-364), same operation order, both pixels at once
-            const f32x2 dy2 = add2(Ay2, pack2(-pyf, -(pyf + 2.0f)));
-            f32x2 t2 = mul2(dy2, mul2(dy2, Bz2));
-            t2 = fma2(dx2, dxcx2, t2);
-            const f32x2 power2 = fma2(t2, mhalf2, mul2(dy2, ndxcy2));
-            float p0, p1;
-            unpack2(power2, p0, p1);
-            float G0 = 0.f, G1 = 0.f, e0 = 0.f, e1 = 0.f, g0 = 0.f, g1 = 0.f;     // masked: a pixel that does not contribute adds zeros
-            if (live0 && !(p0 > 0.0f) && !(p0 < -5.55f && A.z <= 1.0f)) {
-                const float G = SSB_EXPF(p0);
-                const float alpha = fminf(ALPHA_MAX, __fmul_rn(A.z, G));
-                if (!(alpha < ALPHA_MIN)) { g0 = __fmul_rn(c0, grow); G0 = G; e0 = alpha - g0; cnt += (g0 > 0.f) ? 0.f : 1.f; }
-            }
-            if (live1 && !(p1 > 0.0f) && !(p1 < -5.55f && A.z <= 1.0f)) {
-                const float G = SSB_EXPF(p1);
-                const float alpha = fminf(ALPHA_MAX, __fmul_rn(A.z, G));
-                if (!(alpha < ALPHA_MIN)) { g1 = __fmul_rn(c1, grow); G1 = G; e1 = alpha - g1; cnt += (g1 > 0.f) ? 0.f : 1.f; }
-            }
-            const f32x2 err2 = pack2(e0, e1), gp2 = pack2(fmaxf(g0, 0.f), fmaxf(g1, 0.f));
-            l2 = fma2(pack2(-fmaxf(g0, 0.f), -fmaxf(g1, 0.f)), gp2, fma2(err2, err2, l2));        // err^2 - [gt > 0] gt^2
-            const f32x2 w2 = mul2(pack2(G0, G1), err2);                                         // w = G (err - S) T with S = 0, T = 1
-            const f32x2 wx2 = mul2(w2, dx2), wy2 = mul2(w2, dy2);
-            a0 = add2(a0, wx2); a1 = add2(a1, wy2);
-            a2 = fma2(wx2, dx2, a2); a3 = fma2(wx2, dy2, a3); a4 = fma2(wy2, dy2, a4);
-            a5 = add2(a5, w2);
-        }
-        {
-            float lo, hi;
-            unpack2(a0, lo, hi); acc[0] = lo + hi; unpack2(a1, lo, hi); acc[1] = lo + hi; unpack2(a2, lo, hi); acc[2] = lo + hi;
-            unpack2(a3, lo, hi); acc[3] = lo + hi; unpack2(a4, lo, hi); acc[4] = lo + hi; unpack2(a5, lo, hi); acc[5] = lo + hi;
-            unpack2(l2, lo, hi); acc[6] = lo + hi; acc[7] = cnt;
-        }
-#else
         for (int pass0 = vlo; pass0 <= vhi; pass0 += PP) {
             float gtv[PP];
 #pragma unroll
             for (int q = 0; q < PP; q++) {
                 gtv[q] = 0.f;
-                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = __fmul_rn(SSB_GT_COL(gp + 2 * (pass0 + q)), grow);
+                if ((gmask >> (pass0 + q)) & 1u) gtv[q] = SSB_GT_COL(gp + 2 * (pass0 + q)) * grow;
             }
 #pragma unroll
             for (int q = 0; q < PP; q++) {
@@ -425,7 +374,6 @@ __device__ __forceinline__ void tile_one(const SlotSplats& sp, int g, const int4
                 }
             }
         }
-#endif
     }
     reduce_store_partial(acc, part_out, lane);
 }
@@ -473,8 +421,8 @@ __device__ __forceinline__ void tile_two(const SlotSplats& sp, const uint16_t* _
         for (int pass = vlo; pass <= vhi; pass++) {
             const unsigned gm = gmask >> pass;
             float gt0 = 0.f, gt1 = 0.f;
-            if (gm & 1u) gt0 = __fmul_rn(SSB_GT_COL(gptr[0] + 2 * pass), grow[0]);
-            if (gm & 0x100u) gt1 = __fmul_rn(SSB_GT_COL(gptr[1] + 2 * pass), grow[1]);
+            if (gm & 1u) gt0 = SSB_GT_COL(gptr[0] + 2 * pass) * grow[0];
+            if (gm & 0x100u) gt1 = SSB_GT_COL(gptr[1] + 2 * pass) * grow[1];
             const int py = ly0 + 2 * pass;
             if (py < H) {
                 const float pyf = (float)py;
