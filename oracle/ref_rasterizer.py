@@ -78,6 +78,27 @@ class RefState:
             ranges=view(im, io[2], np.uint32, 2 * tiles).reshape(tiles, 2), R=R)
 
 
+def parse_light(st):
+    """RefState.parse() without final_T / n_contrib and without copying the W*H-sized image buffer to the host: every field is
+    sliced on the device first (the million-Gaussian test parses thousands of states)."""
+    P, R = st.P, st.R
+    go = st._layout("ref_geom_layout", st.geom, P, 10)
+    bo = st._layout("ref_binning_layout", st.binning, R, 5)
+    io = st._layout("ref_image_layout", st.img, st.W * st.H, 3)
+    tiles = ((st.W + 15) // 16) * ((st.H + 15) // 16)
+
+    def view(buf, off, dtype, count):
+        n = np.dtype(dtype).itemsize * count
+        return buf[off:off + n].cpu().numpy().view(dtype).copy()
+    return dict(
+        depths=view(st.geom, go[0], np.float32, P), means2D=view(st.geom, go[3], np.float32, 2 * P).reshape(P, 2),
+        cov3D=view(st.geom, go[4], np.float32, 6 * P).reshape(P, 6), conic_opacity=view(st.geom, go[5], np.float32, 4 * P).reshape(P, 4),
+        tiles_touched=view(st.geom, go[7], np.uint32, P), point_offsets=view(st.geom, go[9], np.uint32, P),
+        point_list=view(st.binning, bo[0], np.uint32, R), vals_unsorted=view(st.binning, bo[1], np.uint32, R),
+        keys_sorted=view(st.binning, bo[2], np.uint64, R), keys_unsorted=view(st.binning, bo[3], np.uint64, R),
+        ranges=view(st.img, io[2], np.uint32, 2 * tiles).reshape(tiles, 2), R=R)
+
+
 def rasterize_forward(variant, bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier,
                       cov3D_precomp, viewmatrix, projmatrix, tanfovx, tanfovy, H, W, sh, degree, campos,
                       prefiltered=False, antialiasing=False, debug=False, r_capacity=1 << 16):

@@ -272,3 +272,60 @@ def test_many_gaussians_and_large_lists_bit_exact():
                        W, H, float(case["tanfov"][0, 0]), float(case["tanfov"][0, 1]), dL)
     for k, ok in (("means3D", "dL_dmeans3D"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"), ("features", "dL_dcolors")):
         assert relerr(g[k].reshape(-1), og[ok].reshape(-1)) < 3 * TOL, k
+
+
+def test_a_million_random_gaussians_bin_bit_exactly():
+    """the integer outcome of the projection (radius, tile rectangle => tiles touched, prefix sums, total R) and the
+    depth key bits are step functions of fp32 arithmetic whose contraction into FMAs must match the reference expression for
+    expression -- checked on >= 10^6 random Gaussians (random anisotropic scales, rotations, opacities, positions incl. behind /
+    near the camera plane and off-screen; several random camera rigs of every shape incl. the ragged H36M widths) against the
+    UNMODIFIED reference kernels: 0 mismatches in radii, tiles touched, prefix sums and pair count, the fp32 per-Gaussian state
+    (depth, 2D mean, conic, cov3D) bit-equal for every visible Gaussian, and -- for the views that fit the op's capacity -- the
+    unsorted / sorted keys, values and tile ranges of ~500-Gaussian scenes (thousands of pairs, long tile lists)."""
+    from oracle import ref_rasterizer as refr
+    if not refr.available("h36m"):
+        pytest.skip("oracle/_ref not present on this box")
+    P, total, full_checked = 512, 0, 0
+    rng = np.random.default_rng(77)
+    e = torch.Tensor([]); bg = torch.zeros(32, device=DEV)
+    for name, variant, n_seeds, n_frames in (("h36m", "h36m", 5, 40), ("panoptic", "panoptic", 5, 40), ("occlusion-person-8v", "op", 3, 20)):
+        cfg = configs.get_config(name)
+        C = cfg.n_joints
+        feats = np.zeros((P, C), np.float32); feats[np.arange(P), np.arange(P) % C] = 1.0
+        for seed in range(n_seeds):
+            cams = synthetic.make_cameras(np.random.default_rng(1000 + seed), cfg)
+            means = (rng.normal(size=(n_frames, P, 3)) * np.array([900.0, 900.0, 500.0]) + np.array([0.0, 0.0, 900.0])).astype(np.float32)
+            means[:, :8] *= 6.0                                         # some far off-screen / behind a camera
+            scales = np.exp(rng.uniform(1.0, 4.2, (n_frames, P, 3))).astype(np.float32)
+            rots = rng.normal(size=(n_frames, P, 4)).astype(np.float32); rots /= np.linalg.norm(rots, axis=-1, keepdims=True)
+            opac = rng.uniform(0.05, 1.0, (n_frames, P)).astype(np.float32)
+            for cam in cams:                                            # one batched call per view (own size and field of view)
+                W, H, tfx, tfy = cam.image_width, cam.image_height, float(cam.tanfovx), float(cam.tanfovy)
+                vmv, pmv = t(cam.world_view_transform), t(cam.full_proj_transform)
+                _, radii, _, st = R.rasterize_batched(t(means), t(scales), t(rots), t(opac), t(feats), vmv[None], pmv[None], W, H, tfx, tfy,
+                                                      r_capacity=16384, render_invdepth=False)
+                radii = radii.cpu().numpy()
+                for f in range(n_frames):
+                    Rn, _, rradii, geom, binning, img, _ = refr.rasterize_forward(
+                        variant, bg, t(means[f]), e, t(opac[f]).reshape(-1, 1), t(scales[f]), t(rots[f]), 1.0, e, vmv, pmv, tfx, tfy, H, W,
+                        t(feats).reshape(P, 1, C), 0, t(cam.camera_center), r_capacity=1 << 17)
+                    rs = refr.parse_light(refr.RefState(geom, binning, img, Rn, P, W, H, variant))
+                    hdr = st.header(f)
+                    rr = rradii.cpu().numpy()
+                    assert np.array_equal(radii[f], rr)
+                    assert int(hdr[7]) == Rn                            # the uncapped pair count
+                    if hdr[2] == 0 and f % 4 == 0:                      # fits the capacity: every stage, keys / values / ranges included
+                        ms = st.parse(f, W, H)
+                        assert_stages_equal(ms, rs, radii[f], rr)
+                        full_checked += 1
+                    else:
+                        fld = lambda fid, dt, n: st._field(f, fid, dt, n)
+                        from skelsplat_b200 import lib as L_
+                        assert np.array_equal(fld(L_.F_TILES_TOUCHED, np.uint32, P), rs["tiles_touched"])
+                        assert np.array_equal(fld(L_.F_POINT_OFFSETS, np.uint32, P), rs["point_offsets"])
+                        vis = rr > 0
+                        for fid, k, dt, n, shp in ((L_.F_DEPTHS, "depths", np.float32, P, (P,)), (L_.F_MEANS2D, "means2D", np.float32, 2 * P, (P, 2)),
+                                                   (L_.F_CONIC_OPACITY, "conic_opacity", np.float32, 4 * P, (P, 4)), (L_.F_COV3D, "cov3D", np.float32, 6 * P, (P, 6))):
+                            assert np.array_equal(fld(fid, dt, n).reshape(shp)[vis].view(np.uint32), rs[k][vis].view(np.uint32)), k
+                    total += P
+    assert total >= 1_000_000 and full_checked >= 100, (total, full_checked)
