@@ -21,8 +21,9 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 name = args[0] if args else "h36m"
 F = int(args[1]) if len(args) > 1 else 2048
 cfg = configs.get_config(name)
-seq, host, gt = bench.make_host_batch(cfg, F, seed=100)
-ps = trainer.pack_sequence(cfg, seq.cameras, host["xyz"], None, "cuda", host=host)
+from skelsplat_b200 import setup_gpu
+seq, p2d, init0, gt = bench.make_detection_batch(cfg, F, 0)
+ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, torch.from_numpy(p2d), torch.from_numpy(init0), "cuda")
 lib = L_.lib()
 out = (C.c_ulonglong * 8)()
 trainer.optimize_packed(ps)

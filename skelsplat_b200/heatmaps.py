@@ -18,7 +18,12 @@ Semantics kept literally from the reference:
   * per-channel min-max normalisation with the +1e-8 (general_utils.py:300-304).
 The filter arithmetic follows scipy.ndimage (float64 accumulation, float32 storage
 between the two passes); cupy's float32 accumulation is not reproducible here --
-"parity unpinned" for this setup step, as SURVEY.md section 8c records.
+"parity unpinned" for this setup step, as SURVEY.md section 8c records.  Two decisions
+make the setup exactly reproducible between this specification and the GPU kernels
+(csrc/setup.cu): sigma is evaluated in float64 with a fixed operation order
+(``heatmap_sigmas``), so every integer window agrees; and a patch is stored FACTORED,
+as its column and row profile, the heatmap value being their single fp32 product
+(``HeatmapROIs``) -- the form the fused optimiser reads.
 """
 from dataclasses import dataclass
 
