@@ -294,3 +294,56 @@ def test_closed_form_sorted_positions_on_random_rectangles():
         keys = (xy[:, 1] * gx + xy[:, 0]).astype(np.int64) * (1 << 32) + depth[gs].astype(np.int64)
         expect = np.argsort(keys, kind="stable")                              # emission order breaks ties, as the radix sort does
         assert np.array_equal(np.argsort(pos), expect)
+
+
+def test_sequence_shards_share_the_rig_and_differ_in_frames():
+    """bench.py / multi-GPU runs: rank r optimises shard r of ONE sequence -- same cameras (the scaling loss of round 1 came from
+    giving every rank its own rig), independent frames; shard=None reproduces the plain sequence the reference arm optimises."""
+    cfg = configs.H36M
+    base = synthetic.make_sequence(cfg, 3, seed=100)
+    again = synthetic.make_sequence(cfg, 5, seed=100)
+    s0, s1 = synthetic.make_sequence(cfg, 3, seed=100, shard=0), synthetic.make_sequence(cfg, 3, seed=100, shard=1)
+    for a, b in zip(base.cameras, s1.cameras):
+        assert np.array_equal(a.world_view_transform, b.world_view_transform) and np.array_equal(a.full_proj_transform, b.full_proj_transform)
+    assert all(np.array_equal(x.pose_3d_gt, y.pose_3d_gt) for x, y in zip(base.frames, again.frames))      # a prefix is a prefix
+    assert not np.array_equal(s0.frames[0].pose_3d_gt, s1.frames[0].pose_3d_gt)
+    assert not np.array_equal(s0.frames[0].pose_3d_gt, base.frames[0].pose_3d_gt)
+
+
+def test_adam_step_table_is_torchs_host_arithmetic():
+    """training.adam_step_table: the per-step scalars torch/optim/adam.py forms with python floats -- (lr / bc1) * -1 and bc2 ** 0.5
+    with bc = 1 - beta ** step -- rounded to fp32; the xyz learning rate is the one set at the stepping iteration."""
+    from skelsplat_b200 import training
+    cfg = configs.PANOPTIC
+    ext = 3217.25
+    tab = training.adam_step_table(cfg, ext)
+    lr = trainer.xyz_lr_table(cfg, ext)
+    assert tab.shape == (125, 5) and tab.dtype == np.float32
+    for s in (0, 1, 7, 124):
+        step = s + 1
+        bc1, bc2 = 1 - 0.9 ** step, 1 - 0.999 ** step
+        want = [np.float32((float(lr[step * 4]) / bc1) * -1), np.float32((cfg.scaling_lr / bc1) * -1), np.float32((cfg.rotation_lr / bc1) * -1),
+                np.float32((cfg.opacity_lr / bc1) * -1), np.float32(bc2 ** 0.5)]
+        assert all(a == b for a, b in zip(tab[s], want))
+    assert np.float32(1 - 0.999) != np.float32(1.0) - np.float32(0.999)      # why 1 - beta is formed in fp64 before rounding (csrc/adam_form.h)
+
+
+def test_factored_heatmap_patches():
+    """HeatmapROIs stores a patch as col[h] | row[w]; the heatmap value is their single fp32 product, which is what rois_to_dense
+    materialises, so the dense tensors (drop-in path, reference arm) and the fused kernel see identical bits."""
+    cfg = configs.OCCLUSION_PERSON
+    seq = synthetic.make_sequence(cfg, 1, seed=4)
+    fr = seq.frames[0]
+    _, scal, rot, _ = trainer.initial_raw_state(cfg, fr.pose_3d_init[None])
+    rois = heatmaps.generate_heatmap_rois(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal[0], rot[0])
+    assert rois.data.dtype == np.float32 and rois.data.size == int((rois.rect[..., 2] + rois.rect[..., 3]).sum())
+    dense = heatmaps.rois_to_dense(rois, 1)
+    for j in (0, 7, 14):
+        x0, y0, w, h = rois.rect[1, j]
+        col, row = rois.factors(1, j)
+        assert col.shape == (h,) and row.shape == (w,) and (col > 0).all() and (row > 0).all()
+        want = (col[:, None].astype(np.float32) * row[None, :].astype(np.float32)).astype(np.float32)
+        assert np.array_equal(dense[j, y0:y0 + h, x0:x0 + w], want)
+        assert abs(float(want.max()) - 1.0) < 1e-6
+        dense[j, y0:y0 + h, x0:x0 + w] = 0
+    assert np.array_equal(heatmaps.heatmap_roi_rects(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal[0], rot[0]), rois.rect)
