@@ -35,5 +35,22 @@ l, _ = loss_utils.l2_loss_gaussian(r, g, None); l.backward()
 from fused_ssim import fused_ssim
 a = torch.rand(2, 3, 50, 70, device=dev, requires_grad=True); b = torch.rand(2, 3, 50, 70, device=dev)
 fused_ssim(a, b).backward()
+# the map-form SSIM (FusedSSIMMap: the reference's autograd surface) incl. 'valid' padding
+import fused_ssim as FS
+m = FS.FusedSSIMMap.apply(0.01 ** 2, 0.03 ** 2, a, b, "valid", True); m.sum().backward()
+# the dense loop's iteration bodies + the graph-capturable Adam kernel, launched eagerly (no capture under the sanitizer)
+from skelsplat_b200.training import GraphedFrameOptimizer
+cfg = small_config(configs.OCCLUSION_PERSON_8V, 4)
+seq = synthetic.make_sequence(cfg, 1, seed=5)
+gfo = GraphedFrameOptimizer(cfg, seq.cameras, dev, iterations=16)
+gfo._reset(seq.frames[0].pose_3d_init)
+_, scal0, rot0, _ = trainer.initial_raw_state(cfg, seq.frames[0].pose_3d_init[None])
+from skelsplat_b200 import heatmaps
+gfo.load_heatmaps(rois=heatmaps.generate_heatmap_rois(seq.frames[0].pose_3d_init, seq.frames[0].poses_2d, seq.cameras, scal0[0], rot0[0]))
+for pat in range(gfo.n_patterns):
+    gfo._step_group(pat)
+# the debug accessor of the fused kernel's binning state
+ps = setup_gpu.pack_sequence_gpu(cfg, seq.cameras, np.stack([f.poses_2d for f in seq.frames]).astype(np.float32), None, dev)
+trainer.debug_binning(ps, frame=0, step=1)
 torch.cuda.synchronize()
 print("SANITIZE TARGET DONE")
