@@ -162,13 +162,23 @@ __global__ void roi_rect_kernel(RoiParams p, int* __restrict__ roi_rect, float* 
 // weights term[0 .. 2 radius], 1 / their sum) to a unit delta at pos on an axis of length n:
 //   sum_k w[k] * [reflect(idx + k - radius) == pos].
 __device__ double reflect_response(int idx, int pos, int n, int radius, const double* __restrict__ term, double wsum_inv) {
+    // At most three taps can land on pos: through the mirror below 0 (src = -pos - 1), directly (src = pos) and through the mirror
+    // above n - 1 (src = 2n - 1 - pos).  Their k = src - idx + radius ascend in that order, which is the order the sequential
+    // loop over k (scipy's, and the host specification's) adds them in -- same terms, same order, same bits, O(1) instead of O(radius).
     double acc = 0.0;
-    for (int k = 0; k <= 2 * radius; k++) {
-        int src = idx + k - radius;
-        if (src < 0) src = -src - 1;
-        if (src >= n) src = 2 * n - 1 - src;
-        if (src == pos) acc += term[k] * wsum_inv;
+    if (2 * radius >= n) {                  // window wider than the axis: a tap can be mirrored twice -- the literal loop (never a SkelSplat shape)
+        for (int k = 0; k <= 2 * radius; k++) {
+            int src = idx + k - radius;
+            if (src < 0) src = -src - 1;
+            if (src >= n) src = 2 * n - 1 - src;
+            if (src == pos) acc += term[k] * wsum_inv;
+        }
+        return acc;
     }
+    const int k_lo = -pos - 1 - idx + radius, k_mid = pos - idx + radius, k_hi = 2 * n - 1 - pos - idx + radius;
+    if (k_lo >= 0 && k_lo <= 2 * radius) acc += term[k_lo] * wsum_inv;        // src = -pos - 1 < 0 always
+    if (k_mid >= 0 && k_mid <= 2 * radius) acc += term[k_mid] * wsum_inv;      // src = pos in [0, n)
+    if (k_hi >= 0 && k_hi <= 2 * radius) acc += term[k_hi] * wsum_inv;        // src = 2n - 1 - pos >= n always
     return acc;
 }
 
