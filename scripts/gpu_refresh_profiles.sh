@@ -36,6 +36,13 @@ if [ "$STAGE" = "ncu" ]; then
   ls -la $P
   rm -f gpurun_out/${R}_*.ncu-rep
 fi
+if [ "$STAGE" = "ncu_one" ]; then        # re-capture of the fused optimiser for ONE config (CFG=...); merge its entry into profiles/*_traffic.json by hand
+  P=gpurun_out/profiles_${R}
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:optimize_kernel -c 1 -o gpurun_out/${R}_opt_${CFG} -f python scripts/profile_target.py opt 2048 ${CFG} > gpurun_out/${R}_ncu_opt_${CFG}.log 2>&1
+  python scripts/summarize_ncu.py gpurun_out/${R}_opt_${CFG}.ncu-rep $P/${R}_optimize_kernel_${CFG}_ncu.txt > /dev/null 2>&1
+  python scripts/make_traffic_json.py ${R} $P > /dev/null 2>&1
+  rm -f gpurun_out/${R}_*.ncu-rep
+fi
 if [ "$STAGE" = "ncu_setup" ]; then      # re-capture of the setup kernels only (cheap)
   P=gpurun_out/profiles_${R}
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:roi_|dlt_" -c 4 -o gpurun_out/${R}_setup -f python scripts/profile_target.py setup > gpurun_out/${R}_ncu_setup.log 2>&1
