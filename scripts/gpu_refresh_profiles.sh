@@ -43,6 +43,12 @@ if [ "$STAGE" = "ncu_one" ]; then        # re-capture of the fused optimiser for
   python scripts/make_traffic_json.py ${R} $P > /dev/null 2>&1
   rm -f gpurun_out/${R}_*.ncu-rep
 fi
+if [ "$STAGE" = "ncu_ssim" ]; then
+  P=gpurun_out/profiles_${R}
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:ssim_" -c 6 -o gpurun_out/${R}_ssim -f python scripts/profile_target.py ssim > gpurun_out/${R}_ncu_ssim.log 2>&1
+  python scripts/summarize_ncu.py gpurun_out/${R}_ssim.ncu-rep $P/${R}_ssim_ncu.txt > /dev/null 2>&1
+  rm -f gpurun_out/${R}_*.ncu-rep
+fi
 if [ "$STAGE" = "ncu_setup" ]; then      # re-capture of the setup kernels only (cheap)
   P=gpurun_out/profiles_${R}
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:roi_|dlt_" -c 4 -o gpurun_out/${R}_setup -f python scripts/profile_target.py setup > gpurun_out/${R}_ncu_setup.log 2>&1

@@ -70,8 +70,11 @@ __device__ __forceinline__ float ld0(const float* __restrict__ plane, int y, int
 
 // TRAIN: also write the three derivative maps.  MEAN: do not write the map; accumulate it (inside the `crop` border) into
 // per-warp partial sums instead.
+#ifndef SS_MIN_CTAS
+#define SS_MIN_CTAS 1
+#endif
 template <bool TRAIN, bool MEAN>
-__global__ void __launch_bounds__(SS_WARPS * 32)
+__global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS)
 ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restrict__ img1, const float* __restrict__ img2,
                 float* __restrict__ ssim_map, float* __restrict__ dm_dmu1, float* __restrict__ dm_dsigma1_sq,
                 float* __restrict__ dm_dsigma12, int crop, float* __restrict__ partials)
@@ -228,7 +231,7 @@ constexpr int SS_BWD_STREAMS = 4;    // dm/dmu1, dm/dsigma1^2, dm/dsigma12, dL/d
                                      // cp.async writes and the per-tap reads of a warp are then conflict-free)
 constexpr size_t SS_BWD_SMEM = (size_t)SS_WARPS * SS_NB * (SS_BWD_STREAMS * SS_BUFW_B * sizeof(float) + 32 * sizeof(float2));
 template <bool MEAN>
-__global__ void __launch_bounds__(SS_WARPS * 32)
+__global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS)
 ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const float* __restrict__ img2,
                 const float* __restrict__ dL_dmap, const float* __restrict__ grad_scalar, float scale, int crop,
                 const float* __restrict__ dm_dmu1, const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
