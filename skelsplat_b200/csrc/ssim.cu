@@ -25,10 +25,16 @@
 namespace ssb {
 
 constexpr int SS_R = 5;              // window radius
-constexpr int SS_WARPS = 8;          // warps (= 32-column strips) per CTA
+#ifndef SS_WARPS_PER_CTA
+#define SS_WARPS_PER_CTA 8
+#endif
+#ifndef SS_ROW_BUFFERS
+#define SS_ROW_BUFFERS 8
+#endif
+constexpr int SS_WARPS = SS_WARPS_PER_CTA;   // warps (= 32-column strips) per CTA
 constexpr int SS_ROWS_MAX = 96;      // output rows per warp strip: chosen per launch (ss_rows) so that the strips fill whole waves
 constexpr int SS_BUFW = 48;          // row buffer width (>= 32 + 2*SS_R)
-constexpr int SS_NB = 8;             // row buffers per warp (power of two): SS_NB - 1 rows of cp.async in flight
+constexpr int SS_NB = SS_ROW_BUFFERS; // row buffers per warp (power of two): SS_NB - 1 rows of cp.async in flight
 
 // 11-tap normalised Gaussian, sigma = 1.5: the literal constants of the reference (ssim.cu:9-19); symmetric
 #define SS_G0 0.001028380123898387f
@@ -351,7 +357,7 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
 // Rows per warp strip: every strip costs (rows + 10) input rows; the launch runs ceil(strips / resident warps) rounds of
 // equal strips, so pick the height that minimises rounds x (rows + 10)  (148 SMs x 2 CTAs x 8 warps resident).
 static int ss_rows(int B, int CH, int H, int W) {
-    const long long slots = 148LL * 2 * SS_WARPS;
+    const long long slots = 148LL * 16;          // resident warps: 2 CTAs x 8 warps (or 4 x 4) per SM
     const long long cols = (long long)((W + 32 * SS_WARPS - 1) / (32 * SS_WARPS)) * SS_WARPS * B * CH;   // strips per row band (incl. idle warps)
     long long best_cost = -1; int best = 64;
     for (int rows = 24; rows <= SS_ROWS_MAX; rows++) {
