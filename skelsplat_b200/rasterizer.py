@@ -40,6 +40,7 @@ class _OverflowWatch:
     def __init__(self):
         self.slots = None
         self.i = 0
+        self.gen = [0] * self.N          # a slot is reused after N renders: a ticket older than that is not checked (its data is gone)
 
     def post(self, state_buf):
         if torch.cuda.is_current_stream_capturing():
@@ -48,15 +49,18 @@ class _OverflowWatch:
             self.slots = [(torch.zeros(8, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(self.N)]
         self.i = (self.i + 1) % self.N
         host, ev = self.slots[self.i]
+        ev.synchronize()                 # the slot's previous copy (N renders ago) has long completed; never overwrite one in flight
+        self.gen[self.i] += 1
         host.copy_(state_buf[:32].view(torch.int32), non_blocking=True)
         ev.record()
-        return (self.i, host, ev, state_buf.data_ptr())
+        return (self.i, host, ev, self.gen[self.i])
 
-    @staticmethod
-    def check(ticket, rcap):
+    def check(self, ticket, rcap):
         if ticket is None:
             return
-        _, host, ev, _ = ticket
+        i, host, ev, gen = ticket
+        if self.gen[i] != gen:           # more than N renders between this forward and its backward: the NaN-filled image is the only signal left
+            return
         ev.synchronize()
         if int(host[2]) != 0:
             raise _L.SkelSplatLibraryError(
@@ -246,7 +250,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         if ctx.empty or grad_out_color is None:
             return (None,) * 10
         rs, st = ctx.rs, ctx.st
-        _OverflowWatch.check(ctx.overflow_ticket, st.rcap)
+        _overflow_watch.check(ctx.overflow_ticket, st.rcap)
         m3, sc, ro, cv, op, feats, vm, pm = ctx.saved_tensors
         H, W = int(rs.image_height), int(rs.image_width)
         g = rasterize_batched_backward(st, m3, sc, ro, op, feats, vm, pm, W, H, rs.tanfovx, rs.tanfovy,
