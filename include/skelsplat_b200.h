@@ -160,6 +160,7 @@ int ssb_limb_consistency(int n_frames, int J, const float* xyz, const int* pairs
  * Fused SSIM.  Replaces fused_ssim_cuda.fusedssim / fusedssim_backward
  * (submodules/fused-ssim/ssim.cu:368-444, ssim.h:7-26): 11-tap sigma=1.5 Gaussian window, zero
  * padding.  Tensors are [B,CH,H,W].  dm_* may be NULL when train == 0.
+ * Limits (SSB_ERR_CAPACITY beyond them): B*CH <= 65535 (grid.z), H*W < 2^31 (32-bit index math inside a plane).
  * ------------------------------------------------------------------------------------------ */
 int ssb_fused_ssim_forward(int B, int CH, int H, int W, float C1, float C2, const float* img1, const float* img2,
                            float* ssim_map, float* dm_dmu1, float* dm_dsigma1_sq, float* dm_dsigma12, void* stream);

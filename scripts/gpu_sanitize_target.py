@@ -1,5 +1,5 @@
 """Developer tool: a small pass through every kernel of the library, for compute-sanitizer (memcheck / racecheck).
-   compute-sanitizer --tool memcheck python scripts/gpu_sanitize_target.py"""
+   compute-sanitizer --tool memcheck python scripts/gpu_sanitize_target.py [iterations | ssim]     (ssim: only the loss / SSIM kernels)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
@@ -7,8 +7,9 @@ from skelsplat_b200 import configs, synthetic, trainer, setup_gpu, loss_utils, r
 from tests.util import small_config, raster_case
 
 dev = "cuda"
-it = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-for base in (configs.H36M, configs.PANOPTIC, configs.OCCLUSION_PERSON_8V):
+only_ssim = len(sys.argv) > 1 and sys.argv[1] == "ssim"
+it = int(sys.argv[1]) if len(sys.argv) > 1 and not only_ssim else 8
+for base in (() if only_ssim else (configs.H36M, configs.PANOPTIC, configs.OCCLUSION_PERSON_8V)):
     cfg = small_config(base, 4)
     seq = synthetic.make_sequence(cfg, 2, seed=3)
     p2 = np.stack([f.poses_2d for f in seq.frames]).astype(np.float32)
@@ -38,6 +39,12 @@ fused_ssim(a, b).backward()
 # the map-form SSIM (FusedSSIMMap: the reference's autograd surface) incl. 'valid' padding
 import fused_ssim as FS
 m = FS.FusedSSIMMap.apply(0.01 ** 2, 0.03 ** 2, a, b, "valid", True); m.sum().backward()
+for shape in ((1, 1, 13, 9), (1, 2, 97, 131), (2, 1, 33, 300)):      # ragged edges: partial strips, W < 32, H < one strip
+    a = torch.rand(*shape, device=dev, requires_grad=True); b = torch.rand(*shape, device=dev)
+    fused_ssim(a, b).backward(); fused_ssim(a.detach(), b, train=False)
+    FS.FusedSSIMMap.apply(0.01 ** 2, 0.03 ** 2, a, b, "same", True).sum().backward()
+if only_ssim:
+    torch.cuda.synchronize(); print("SANITIZE TARGET DONE (ssim only)"); sys.exit(0)
 # the dense loop's iteration bodies + the graph-capturable Adam kernel, launched eagerly (no capture under the sanitizer)
 from skelsplat_b200.training import GraphedFrameOptimizer
 cfg = small_config(configs.OCCLUSION_PERSON_8V, 4)

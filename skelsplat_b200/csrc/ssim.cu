@@ -31,6 +31,12 @@ constexpr int SS_R = 5;              // window radius
 #ifndef SS_ROW_BUFFERS
 #define SS_ROW_BUFFERS 8
 #endif
+#ifndef SS_SYMMETRIC_TAPS
+#define SS_SYMMETRIC_TAPS 1
+#endif
+#ifndef SS_BWD_PAIRED
+#define SS_BWD_PAIRED 1
+#endif
 constexpr int SS_WARPS = SS_WARPS_PER_CTA;   // warps (= 32-column strips) per CTA
 constexpr int SS_ROWS_MAX = 96;      // output rows per warp strip: chosen per launch (ss_rows) so that the strips fill whole waves
 constexpr int SS_BUFW = 48;          // row buffer width (>= 32 + 2*SS_R)
@@ -58,6 +64,7 @@ __device__ __forceinline__ float rcp_nr(float x) {
 // keeps a loop-invariant value in its register: without it ptxas re-derives lane / warp / block indices from the special
 // registers in every unrolled row (~40 extra instructions per row)
 #define SS_KEEP(v) asm volatile("" : "+r"(v))
+#define SS_KEEP_PTR(p) asm volatile("" : "+l"(p))      // a finished 64-bit plane pointer, so that p + int is ONE IMAD.WIDE
 
 // cp.async (LDGSTS): 4-byte global -> shared copies that bypass the register file; src_bytes = 0 zero-fills (zero padding,
 // rows / columns outside the image).  Each warp keeps SS_NB - 1 input rows in flight: with one row of register prefetch the
@@ -78,6 +85,9 @@ __device__ __forceinline__ float ld0(const float* __restrict__ plane, int y, int
 // per-warp partial sums instead.
 #ifndef SS_MIN_CTAS
 #define SS_MIN_CTAS 1
+#endif
+#ifndef SS_MIN_CTAS_BWD
+#define SS_MIN_CTAS_BWD SS_MIN_CTAS
 #endif
 template <bool TRAIN, bool MEAN>
 __global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS)
@@ -112,17 +122,22 @@ ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restr
         for (int k = 0; k < 6; k++) gg[k] = pack2(ss_g(k), ss_g(k));
         f32x2 ring_m[11], ring_e[11];                                  // (mu1, mu2), (E[x^2], E[y^2]) after the horizontal pass
         float ring_x[11];                                              // E[xy]
-        // input element (y0 - 5 + row, xa) of both images; clamped to the plane when outside (never read then: src size 0)
+        // input element (y0 - 5 + row, xa) of both images.  Addresses are formed from CLAMPED coordinates with 32-bit index math
+        // inside the plane (H * W < 2^31, checked by the host): always in bounds, one IMAD + one IMAD.WIDE per copy instead of a
+        // 64-bit multiply, two selects and a shift/add pair (the address arithmetic was a quarter of the instructions of a row)
         const float* p1 = img1 + plane;
         const float* p2 = img2 + plane;
+        SS_KEEP_PTR(p1); SS_KEEP_PTR(p2);
+        int xac = min(max(xa, 0), W - 1), xbc = min(max(xb, 0), W - 1);
+        SS_KEEP(xac); SS_KEEP(xbc);
         size_t o = plane + (size_t)y0 * W + px;                        // output element of the current output row
         auto issue_row = [&](int row) {                                // input row `row` of this strip -> ring slot row % SS_NB
             const int y = y0 - SS_R + row;
             const bool yv = (unsigned)y < (unsigned)H && row < n_in;
-            const ptrdiff_t base = yv ? (ptrdiff_t)y * W : 0;
+            const int rowoff = min(max(y, 0), H - 1) * W;
             float2* dst = mybuf + (row & (SS_NB - 1)) * SS_BUFW;
             const bool va_ = yv && ca, vb_ = yv && cb;
-            const ptrdiff_t ia = va_ ? base + xa : 0, ib_ = vb_ ? base + xb : 0;
+            const int ia = rowoff + xac, ib_ = rowoff + xbc;
             cp_async4(&dst->x, p1 + ia, va_);
             cp_async4(&dst->y, p2 + ia, va_);
             if (lo10) {
@@ -148,6 +163,25 @@ ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restr
                     // FMA latency x issue, not by memory)
                     f32x2 hm = 0ull, he = 0ull, hm1 = 0ull, he1 = 0ull;
                     float hx = 0.f, hx1 = 0.f;
+#if SS_SYMMETRIC_TAPS
+                    // the window is symmetric: taps k and 10 - k share a weight, so their squares / products are summed first
+                    // (fma(p, p, q*q): 3 instructions per tap pair and moment instead of 4) -- 45 instead of 55 per row
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        const float2 uv = buf[k], wz = buf[10 - k];
+                        const f32x2 p = pack2(uv.x, uv.y), q = pack2(wz.x, wz.y);
+                        const f32x2 g2 = gg[k];
+                        const f32x2 sm = add2(p, q), se = fma2(p, p, mul2(q, q));
+                        const float sx = fmaf(uv.x, uv.y, wz.x * wz.y);
+                        if (k & 1) { hm1 = fma2(g2, sm, hm1); he1 = fma2(g2, se, he1); hx1 = fmaf(ss_g(k), sx, hx1); }
+                        else { hm = fma2(g2, sm, hm); he = fma2(g2, se, he); hx = fmaf(ss_g(k), sx, hx); }
+                    }
+                    {
+                        const float2 uv = buf[5];
+                        const f32x2 p = pack2(uv.x, uv.y);
+                        hm1 = fma2(gg[5], p, hm1); he1 = fma2(gg[5], mul2(p, p), he1); hx1 = fmaf(ss_g(5), uv.x * uv.y, hx1);
+                    }
+#else
 #pragma unroll
                     for (int k = 0; k < 11; k++) {
                         const float2 uv = buf[k];
@@ -156,6 +190,7 @@ ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restr
                         if (k & 1) { hm1 = fma2(g2, p, hm1); he1 = fma2(g2, mul2(p, p), he1); hx1 = fmaf(ss_g(k), uv.x * uv.y, hx1); }
                         else { hm = fma2(g2, p, hm); he = fma2(g2, mul2(p, p), he); hx = fmaf(ss_g(k), uv.x * uv.y, hx); }
                     }
+#endif
                     const f32x2 one2 = pack2(1.0f, 1.0f);
                     ring_m[ii] = fma2(hm1, one2, hm); ring_e[ii] = fma2(he1, one2, he); ring_x[ii] = hx + hx1;
                     if (i >= 2 * SS_R) {
@@ -237,7 +272,7 @@ constexpr int SS_BWD_STREAMS = 4;    // dm/dmu1, dm/dsigma1^2, dm/dsigma12, dL/d
                                      // cp.async writes and the per-tap reads of a warp are then conflict-free)
 constexpr size_t SS_BWD_SMEM = (size_t)SS_WARPS * SS_NB * (SS_BWD_STREAMS * SS_BUFW_B * sizeof(float) + 32 * sizeof(float2));
 template <bool MEAN>
-__global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS)
+__global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS_BWD)
 ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const float* __restrict__ img2,
                 const float* __restrict__ dL_dmap, const float* __restrict__ grad_scalar, float scale, int crop,
                 const float* __restrict__ dm_dmu1, const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
@@ -277,24 +312,42 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
     const float* q0 = MEAN ? nullptr : dL_dmap + plane;
     const float* i1 = img1 + plane;
     const float* i2 = img2 + plane;
+    SS_KEEP_PTR(q1); SS_KEEP_PTR(q2); SS_KEEP_PTR(q3); SS_KEEP_PTR(i1); SS_KEEP_PTR(i2);
+    if (!MEAN) SS_KEEP_PTR(q0);
     // one commit group per row index: the input row `row` of the strip AND the two image values the output row finished in the
     // same iteration (row - 10) needs -- so the epilogue never waits on a global load
+    // (addresses from clamped coordinates, 32-bit index math inside the plane: see the forward kernel)
+    int xac = min(max(xa, 0), W - 1), xbc = min(max(xb, 0), W - 1), pxc = min(px, W - 1);
+    SS_KEEP(xac); SS_KEEP(xbc); SS_KEEP(pxc);
     auto issue_row = [&](int row) {
         const int y = y0 - SS_R + row;
         const bool yv = y >= crop && y < H - crop && row < n_in;
-        const ptrdiff_t base = yv ? (ptrdiff_t)y * W : 0;
+        const int rowoff = min(max(y, 0), H - 1) * W;
         float* dst = mybuf + (row & (SS_NB - 1)) * RS;
         const bool va_ = yv && ca, vb_ = yv && cb;
-        const ptrdiff_t ia = va_ ? base + xa : 0, ib_ = vb_ ? base + xb : 0;
+        const int ia = rowoff + xac, ib_ = rowoff + xbc;
+#if SS_BWD_PAIRED
+        // ring row = float2 (dm/dmu1, dm/dsigma1^2)[SS_BUFW_B] | float2 (dm/dsigma12, dL/dmap)[SS_BUFW_B] (MEAN: the second array
+        // is a plain float array): one LDS.64 per tap delivers the packed pair the FFMA2 consumes
+        float* dcd = dst + 2 * SS_BUFW_B + (MEAN ? 0 : lane);           // dst already carries + lane floats; the float2 arrays need + 2 lane
+        float* dab = dst + lane;
+        cp_async4(dab, q1 + ia, va_); cp_async4(dab + 1, q2 + ia, va_); cp_async4(dcd, q3 + ia, va_);
+        if (!MEAN) cp_async4(dcd + 1, q0 + ia, va_);
+        if (lo10) {
+            cp_async4(dab + 64, q1 + ib_, vb_); cp_async4(dab + 65, q2 + ib_, vb_); cp_async4(dcd + (MEAN ? 32 : 64), q3 + ib_, vb_);
+            if (!MEAN) cp_async4(dcd + 65, q0 + ib_, vb_);
+        }
+#else
         cp_async4(dst, q1 + ia, va_); cp_async4(dst + SS_BUFW_B, q2 + ia, va_); cp_async4(dst + 2 * SS_BUFW_B, q3 + ia, va_);
         if (!MEAN) cp_async4(dst + 3 * SS_BUFW_B, q0 + ia, va_);
         if (lo10) {
             cp_async4(dst + 32, q1 + ib_, vb_); cp_async4(dst + SS_BUFW_B + 32, q2 + ib_, vb_); cp_async4(dst + 2 * SS_BUFW_B + 32, q3 + ib_, vb_);
             if (!MEAN) cp_async4(dst + 3 * SS_BUFW_B + 32, q0 + ib_, vb_);
         }
+#endif
         const int yo = y0 + row - 2 * SS_R;
         const bool vo = row >= 2 * SS_R && row < n_in && cw;
-        const ptrdiff_t io = vo ? (ptrdiff_t)yo * W + px : 0;
+        const int io = min(max(yo, 0), H - 1) * W + pxc;
         float2* pd = mypix + (row & (SS_NB - 1)) * 32;
         cp_async4(&pd->x, i1 + io, vo); cp_async4(&pd->y, i2 + io, vo);
         cp_async_commit();
@@ -319,8 +372,15 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
                 const f32x2 one2 = pack2(1.0f, 1.0f);
 #pragma unroll
                 for (int k = 0; k < 11; k++) {
+#if SS_BWD_PAIRED
+                    const float2 tab = reinterpret_cast<const float2*>(buf + lane)[k];
+                    float ta = tab.x, tb = tab.y, tc;
+                    if (MEAN) tc = buf[2 * SS_BUFW_B + k];
+                    else { const float2 tcd = reinterpret_cast<const float2*>(buf + 2 * SS_BUFW_B + lane)[k]; tc = tcd.x * tcd.y; ta *= tcd.y; tb *= tcd.y; }
+#else
                     float ta = buf[k], tb = buf[SS_BUFW_B + k], tc = buf[2 * SS_BUFW_B + k];
                     if (!MEAN) { const float dl = buf[3 * SS_BUFW_B + k]; ta *= dl; tb *= dl; tc *= dl; }
+#endif
                     if (k & 1) { hab1 = fma2(gg[k <= 5 ? k : 10 - k], pack2(ta, tb), hab1); hc1 = fmaf(ss_g(k), tc, hc1); }
                     else { hab = fma2(gg[k <= 5 ? k : 10 - k], pack2(ta, tb), hab); hc = fmaf(ss_g(k), tc, hc); }
                 }
@@ -399,7 +459,7 @@ int ssb_fused_ssim_forward(int B, int CH, int H, int W, float C1, float C2, cons
     if ((size_t)B * CH * H * W == 0) return SSB_OK;
     if (!img1 || !img2 || !ssim_map) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
-    if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
+    if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
     const int rows = ss_rows(B, CH, H, W);
     const dim3 grid = ss_grid(B, CH, H, W, rows);
     cudaStream_t st = (cudaStream_t)stream_;
@@ -415,7 +475,7 @@ int ssb_fused_ssim_backward(int B, int CH, int H, int W, float C1, float C2, con
     if (B < 0 || CH < 0 || H < 0 || W < 0) return SSB_ERR_INVALID;
     if ((size_t)B * CH * H * W == 0) return SSB_OK;
     if (!img1 || !img2 || !dL_dmap || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) return SSB_ERR_INVALID;
-    if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
+    if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
     const int rows = ss_rows(B, CH, H, W);
     return ssb_set_cuda_error(ss_launch_bwd<false>(ss_grid(B, CH, H, W, rows), (cudaStream_t)stream_, H, W, rows, img1, img2, dL_dmap, nullptr, 0.f, 0,
                                                    dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1));
@@ -432,7 +492,7 @@ int ssb_fused_ssim_mean_forward(int B, int CH, int H, int W, float C1, float C2,
     if ((size_t)B * CH * H * W == 0 || H <= 2 * crop || W <= 2 * crop) return SSB_ERR_INVALID;
     if (!img1 || !img2 || !mean_out || !workspace) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
-    if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
+    if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
     const int rows = ss_rows(B, CH, H, W);
     const dim3 grid = ss_grid(B, CH, H, W, rows);
     cudaStream_t st = (cudaStream_t)stream_;
@@ -449,7 +509,7 @@ int ssb_fused_ssim_mean_backward(int B, int CH, int H, int W, const float* img1,
     if (B < 0 || CH < 0 || H < 0 || W < 0 || crop < 0) return SSB_ERR_INVALID;
     if ((size_t)B * CH * H * W == 0 || H <= 2 * crop || W <= 2 * crop) return SSB_ERR_INVALID;
     if (!img1 || !img2 || !grad_mean || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) return SSB_ERR_INVALID;
-    if ((long long)B * CH > 65535) return SSB_ERR_CAPACITY;
+    if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
     const double count = (double)B * CH * (double)(H - 2 * crop) * (double)(W - 2 * crop);
     const int rows = ss_rows(B, CH, H, W);
     return ssb_set_cuda_error(ss_launch_bwd<true>(ss_grid(B, CH, H, W, rows), (cudaStream_t)stream_, H, W, rows, img1, img2, nullptr, grad_mean,

@@ -17,6 +17,7 @@ Differences, all deliberate:
 Batched entry points (`rasterize_batched`) expose the frames x views form used by the bench.
 """
 import ctypes as C
+import os
 from typing import NamedTuple, Optional
 
 import numpy as np
@@ -24,8 +25,6 @@ import torch
 import torch.nn as nn
 
 from . import lib as _L
-
-import os
 
 DEFAULT_R_CAPACITY = int(os.environ.get("SKELSPLAT_B200_R_CAPACITY", 2048))     # (Gaussian,tile) pairs per view of the drop-in op
 MAX_R_CAPACITY = 1 << 14                                                        # ssb_rasterize_forward's upper bound
