@@ -10,10 +10,14 @@
 // owns a 32-column strip and marches down the rows (no block-level barrier at all):
 //   * horizontal pass: the row's 42 input pixels of both images go through a per-warp (u,v)-interleaved row buffer, so one
 //     LDS.64 per tap delivers the (u,v) pair; the five moments are accumulated with PACKED fp32 math (FFMA2 / FMUL2,
-//     `fma.rn.f32x2`, new on sm_100): (mu1,mu2) and (E[x^2],E[y^2]) as pairs, E[xy] alone -- 6 instructions per tap;
+//     `fma.rn.f32x2`, new on sm_100): (mu1,mu2) and (E[x^2],E[y^2]) as pairs, E[xy] alone; taps k and 10 - k share a weight, so
+//     their squares / products are summed first -- 45 instructions per output pixel;
 //   * vertical pass: the last 11 horizontal results live in a REGISTER ring (the row loop is unrolled by 11 so every ring
 //     index is static): 3 instructions per tap, no shared memory, and a finished output row every input row;
-//   * the next input row's global loads are issued before the current row's math (one row of software prefetch);
+//   * input rows arrive by cp.async (4-byte LDGSTS, zero-filling the padding) into a ring of SS_NB row buffers per warp, SS_NB - 1
+//     rows in flight; copy addresses come from clamped coordinates with 32-bit index math (one IMAD.WIDE per copy);
+//   * the backward kernel gives every lane TWO adjacent columns of a 64-column strip: the 12 ring values per stream serve both
+//     and arrive as LDS.128 / LDS.64 (the one-column form was bound by the shared-memory pipe);
 //   * `fused_ssim()` only ever consumes map.mean(): the MEAN variants reduce the map in the kernel (per-warp partial sums,
 //     summed in a fixed order in fp64 by a tiny second kernel) and take dL/dmap as the scalar it is, so neither the map nor
 //     dL/dmap ever touches HBM (train step: 495 MB instead of 675 MB at 5x1x1500x1500).
@@ -31,13 +35,17 @@ constexpr int SS_R = 5;              // window radius
 #ifndef SS_ROW_BUFFERS
 #define SS_ROW_BUFFERS 8
 #endif
+#ifndef SS_WARPS_PER_CTA_BWD
+#define SS_WARPS_PER_CTA_BWD SS_WARPS_PER_CTA
+#endif
+#ifndef SS_BWD_RESIDENT_WARPS
+#define SS_BWD_RESIDENT_WARPS 16     // warps per SM the backward launch keeps resident (CTAs per SM x warps per CTA): sizes the strips
+#endif
 #ifndef SS_SYMMETRIC_TAPS
 #define SS_SYMMETRIC_TAPS 1
 #endif
-#ifndef SS_BWD_PAIRED
-#define SS_BWD_PAIRED 1
-#endif
-constexpr int SS_WARPS = SS_WARPS_PER_CTA;   // warps (= 32-column strips) per CTA
+constexpr int SS_WARPS = SS_WARPS_PER_CTA;   // warps (= 32-column strips) per CTA, forward
+constexpr int SS_WARPS_B = SS_WARPS_PER_CTA_BWD;   // warps (= 64-column strips) per CTA, backward
 constexpr int SS_ROWS_MAX = 96;      // output rows per warp strip: chosen per launch (ss_rows) so that the strips fill whole waves
 constexpr int SS_BUFW = 48;          // row buffer width (>= 32 + 2*SS_R)
 constexpr int SS_NB = SS_ROW_BUFFERS; // row buffers per warp (power of two): SS_NB - 1 rows of cp.async in flight
@@ -87,8 +95,8 @@ __device__ __forceinline__ float ld0(const float* __restrict__ plane, int y, int
 #define SS_MIN_CTAS 1
 #endif
 #ifndef SS_MIN_CTAS_BWD
-#define SS_MIN_CTAS_BWD SS_MIN_CTAS
-#endif
+#define SS_MIN_CTAS_BWD 2            // backward (two columns per lane): two 8-warp CTAs per SM at <= 128 registers; measured equal
+#endif                               // (+-2 %) to 12 warps x 1 CTA at 140 registers and to 8 warps x 1 CTA at 158
 template <bool TRAIN, bool MEAN>
 __global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS)
 ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restrict__ img1, const float* __restrict__ img2,
@@ -266,43 +274,55 @@ ssim_mean_finalize_kernel(const float* __restrict__ partials, long long n, doubl
 // Backward: dL/dimg1 = conv(dL dm/dmu1) + 2 img1 conv(dL dm/dsigma1^2) + img2 conv(dL dm/dsigma12)   (ssim.cu:288-366).
 // MEAN: dL/dmap is the scalar *grad_scalar * scale inside the crop border and 0 outside: never materialised -- the border is
 // zero-filled by the copies and the scalar is applied after the convolutions.
-constexpr int SS_BUFW_B = 44;        // >= 32 + 2*SS_R
-// dynamic shared memory per CTA: per warp a ring of SS_NB input rows (float4) + SS_NB rows of (img1, img2) at the output pixels
-constexpr int SS_BWD_STREAMS = 4;    // dm/dmu1, dm/dsigma1^2, dm/dsigma12, dL/dmap: one float array each (structure of arrays: the 4-byte
-                                     // cp.async writes and the per-tap reads of a warp are then conflict-free)
-constexpr size_t SS_BWD_SMEM = (size_t)SS_WARPS * SS_NB * (SS_BWD_STREAMS * SS_BUFW_B * sizeof(float) + 32 * sizeof(float2));
+//
+// A warp owns a 64-column strip and every lane TWO adjacent output columns: the 12 ring values a lane reads per row and stream
+// serve both columns and start at an even index, so they arrive as 6 LDS.128 (+ 6 LDS.64) instead of 2 x 11 scalar loads -- the
+// one-column form of this kernel was bound by the shared-memory pipe (ncu: LSU 56 %, `mio_throttle` the top stall).  The copies
+// keep the coalesced mapping (lane -> column lane, lane + 32, halo lane + 64).
+constexpr int SS_BW2 = 76;           // ring row width in pixels: 64 + 2*SS_R = 74, padded so that every array stays 16-byte aligned
+// ring row: float2 (dm/dmu1, dm/dsigma1^2)[SS_BW2] | MEAN: float dm/dsigma12[SS_BW2]; else float2 (dm/dsigma12, dL/dmap)[SS_BW2]
+template <bool MEAN> __host__ __device__ constexpr int ss_bwd_row_floats() { return (MEAN ? 3 : 4) * SS_BW2; }
+// dynamic shared memory per CTA: per warp a ring of SS_NB input rows + SS_NB rows of (img1, img2) at the 64 output pixels
+template <bool MEAN> constexpr size_t ss_bwd_smem() { return (size_t)SS_WARPS_B * SS_NB * (ss_bwd_row_floats<MEAN>() * sizeof(float) + 64 * sizeof(float2)); }
+
 template <bool MEAN>
-__global__ void __launch_bounds__(SS_WARPS * 32, SS_MIN_CTAS_BWD)
+__global__ void __launch_bounds__(SS_WARPS_B * 32, SS_MIN_CTAS_BWD)
 ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const float* __restrict__ img2,
                 const float* __restrict__ dL_dmap, const float* __restrict__ grad_scalar, float scale, int crop,
                 const float* __restrict__ dm_dmu1, const float* __restrict__ dm_dsigma1_sq, const float* __restrict__ dm_dsigma12,
                 float* __restrict__ dL_dimg1)
 {
     extern __shared__ __align__(16) unsigned char ss_dyn[];
-    float (*s_row)[SS_NB][SS_BWD_STREAMS][SS_BUFW_B] = reinterpret_cast<float (*)[SS_NB][SS_BWD_STREAMS][SS_BUFW_B]>(ss_dyn);
-    float2 (*s_pix)[SS_NB][32] = reinterpret_cast<float2 (*)[SS_NB][32]>(ss_dyn + (size_t)SS_WARPS * SS_NB * SS_BWD_STREAMS * SS_BUFW_B * sizeof(float));
+    constexpr int RS = ss_bwd_row_floats<MEAN>();          // floats per ring row
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SS_KEEP(lane); SS_KEEP(warp);
+    float* ring = reinterpret_cast<float*>(ss_dyn) + (size_t)warp * SS_NB * RS;
+    float2* pixring = reinterpret_cast<float2*>(ss_dyn + (size_t)SS_WARPS_B * SS_NB * RS * sizeof(float)) + (size_t)warp * SS_NB * 64;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    int x0 = (blockIdx.x * SS_WARPS + warp) * 32, y0 = blockIdx.y * rows;
+    int x0 = (blockIdx.x * SS_WARPS_B + warp) * 64, y0 = blockIdx.y * rows;
     SS_KEEP(x0); SS_KEEP(y0);
     if (x0 >= W) return;
     const float gs = MEAN ? __ldg(grad_scalar) * scale : 1.f;
     const int n_out = min(rows, H - y0);
     const int n_in = n_out + 2 * SS_R;
-    const int xa = x0 - SS_R + lane, xb = xa + 32;
-    const int px = x0 + lane;
+    // copies: the lane brings in ring columns lane, lane + 32 and (lane < 10) lane + 64 = image columns xa, xa + 32, xa + 64, and
+    // the (img1, img2) values of output columns x0 + lane, x0 + 32 + lane
+    const int xa = x0 - SS_R + lane, xb = xa + 32, xc = xa + 64;
+    const int pa = x0 + lane, pb = pa + 32;
+    const int px = x0 + 2 * lane;                           // the lane's two OUTPUT columns: px, px + 1
     // a column contributes if it is inside the image and (MEAN) inside the crop border
-    int flags = ((xa >= crop && xa < W - crop) ? 1 : 0) | ((lane < 2 * SS_R && xb >= crop && xb < W - crop) ? 2 : 0) | (px < W ? 4 : 0) |
-                (lane < 2 * SS_R ? 8 : 0);
+    int flags = ((xa >= crop && xa < W - crop) ? 1 : 0) | ((xb >= crop && xb < W - crop) ? 2 : 0) |
+                ((lane < 2 * SS_R && xc >= crop && xc < W - crop) ? 4 : 0) | (lane < 2 * SS_R ? 8 : 0) |
+                (px < W ? 16 : 0) | (px + 1 < W ? 32 : 0) | (pa < W ? 64 : 0) | (pb < W ? 128 : 0);
     SS_KEEP(flags);
 #define ca (flags & 1)
 #define cb (flags & 2)
-#define cw (flags & 4)
+#define cc (flags & 4)
 #define lo10 (flags & 8)
-    float* mybuf = &s_row[warp][0][0][lane];
-    float2* mypix = &s_pix[warp][0][lane];
-    constexpr int RS = SS_BWD_STREAMS * SS_BUFW_B;      // floats per ring row
+#define cw0 (flags & 16)
+#define cw1 (flags & 32)
+#define cpa (flags & 64)
+#define cpb (flags & 128)
     f32x2 gg[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) gg[k] = pack2(ss_g(k), ss_g(k));
@@ -314,49 +334,44 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
     const float* i2 = img2 + plane;
     SS_KEEP_PTR(q1); SS_KEEP_PTR(q2); SS_KEEP_PTR(q3); SS_KEEP_PTR(i1); SS_KEEP_PTR(i2);
     if (!MEAN) SS_KEEP_PTR(q0);
-    // one commit group per row index: the input row `row` of the strip AND the two image values the output row finished in the
-    // same iteration (row - 10) needs -- so the epilogue never waits on a global load
     // (addresses from clamped coordinates, 32-bit index math inside the plane: see the forward kernel)
-    int xac = min(max(xa, 0), W - 1), xbc = min(max(xb, 0), W - 1), pxc = min(px, W - 1);
-    SS_KEEP(xac); SS_KEEP(xbc); SS_KEEP(pxc);
+    int xac = min(max(xa, 0), W - 1), xbc = min(max(xb, 0), W - 1), xcc = min(max(xc, 0), W - 1), pac = min(pa, W - 1), pbc = min(pb, W - 1);
+    SS_KEEP(xac); SS_KEEP(xbc); SS_KEEP(xcc); SS_KEEP(pac); SS_KEEP(pbc);
+    // one commit group per row index: the input row `row` of the strip AND the image values the output row finished in the
+    // same iteration (row - 10) needs -- so the epilogue never waits on a global load
     auto issue_row = [&](int row) {
         const int y = y0 - SS_R + row;
         const bool yv = y >= crop && y < H - crop && row < n_in;
         const int rowoff = min(max(y, 0), H - 1) * W;
-        float* dst = mybuf + (row & (SS_NB - 1)) * RS;
-        const bool va_ = yv && ca, vb_ = yv && cb;
-        const int ia = rowoff + xac, ib_ = rowoff + xbc;
-#if SS_BWD_PAIRED
-        // ring row = float2 (dm/dmu1, dm/dsigma1^2)[SS_BUFW_B] | float2 (dm/dsigma12, dL/dmap)[SS_BUFW_B] (MEAN: the second array
-        // is a plain float array): one LDS.64 per tap delivers the packed pair the FFMA2 consumes
-        float* dcd = dst + 2 * SS_BUFW_B + (MEAN ? 0 : lane);           // dst already carries + lane floats; the float2 arrays need + 2 lane
-        float* dab = dst + lane;
+        float* dst = ring + (row & (SS_NB - 1)) * RS;
+        const bool va_ = yv && ca, vb_ = yv && cb, vc_ = yv && cc;
+        const int ia = rowoff + xac, ib_ = rowoff + xbc, ic_ = rowoff + xcc;
+        float* dab = dst + 2 * lane;                                     // float2 (a, b)[lane]
+        float* dcd = dst + 2 * SS_BW2 + (MEAN ? lane : 2 * lane);        // float c[lane]  /  float2 (c, dl)[lane]
+        constexpr int CS = MEAN ? 1 : 2;                                 // floats per pixel of the second array
         cp_async4(dab, q1 + ia, va_); cp_async4(dab + 1, q2 + ia, va_); cp_async4(dcd, q3 + ia, va_);
         if (!MEAN) cp_async4(dcd + 1, q0 + ia, va_);
+        cp_async4(dab + 64, q1 + ib_, vb_); cp_async4(dab + 65, q2 + ib_, vb_); cp_async4(dcd + 32 * CS, q3 + ib_, vb_);
+        if (!MEAN) cp_async4(dcd + 32 * CS + 1, q0 + ib_, vb_);
         if (lo10) {
-            cp_async4(dab + 64, q1 + ib_, vb_); cp_async4(dab + 65, q2 + ib_, vb_); cp_async4(dcd + (MEAN ? 32 : 64), q3 + ib_, vb_);
-            if (!MEAN) cp_async4(dcd + 65, q0 + ib_, vb_);
+            cp_async4(dab + 128, q1 + ic_, vc_); cp_async4(dab + 129, q2 + ic_, vc_); cp_async4(dcd + 64 * CS, q3 + ic_, vc_);
+            if (!MEAN) cp_async4(dcd + 64 * CS + 1, q0 + ic_, vc_);
         }
-#else
-        cp_async4(dst, q1 + ia, va_); cp_async4(dst + SS_BUFW_B, q2 + ia, va_); cp_async4(dst + 2 * SS_BUFW_B, q3 + ia, va_);
-        if (!MEAN) cp_async4(dst + 3 * SS_BUFW_B, q0 + ia, va_);
-        if (lo10) {
-            cp_async4(dst + 32, q1 + ib_, vb_); cp_async4(dst + SS_BUFW_B + 32, q2 + ib_, vb_); cp_async4(dst + 2 * SS_BUFW_B + 32, q3 + ib_, vb_);
-            if (!MEAN) cp_async4(dst + 3 * SS_BUFW_B + 32, q0 + ib_, vb_);
-        }
-#endif
         const int yo = y0 + row - 2 * SS_R;
-        const bool vo = row >= 2 * SS_R && row < n_in && cw;
-        const int io = min(max(yo, 0), H - 1) * W + pxc;
-        float2* pd = mypix + (row & (SS_NB - 1)) * 32;
-        cp_async4(&pd->x, i1 + io, vo); cp_async4(&pd->y, i2 + io, vo);
+        const bool vo = row >= 2 * SS_R && row < n_in;
+        const int orow = min(max(yo, 0), H - 1) * W;
+        float2* pd = pixring + (row & (SS_NB - 1)) * 64 + lane;
+        const bool voa = vo && cpa, vob = vo && cpb;
+        cp_async4(&pd->x, i1 + (orow + pac), voa); cp_async4(&pd->y, i2 + (orow + pac), voa);
+        cp_async4(&pd[32].x, i1 + (orow + pbc), vob); cp_async4(&pd[32].y, i2 + (orow + pbc), vob);
         cp_async_commit();
     };
-    f32x2 ring_ab[11];
-    float ring_c[11];
+    f32x2 ring_ab[2][11];
+    float ring_c[2][11];
 #pragma unroll
     for (int r = 0; r < SS_NB - 1; r++) issue_row(r);
     size_t o = plane + (size_t)y0 * W + px;
+    const f32x2 one2 = pack2(1.0f, 1.0f);
 #pragma unroll 1
     for (int ib = 0; ib < n_in; ib += 11) {
 #pragma unroll
@@ -366,42 +381,55 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
                 cp_async_wait<SS_NB - 2>();
                 __syncwarp();
                 issue_row(i + SS_NB - 1);
-                const float* buf = mybuf + (i & (SS_NB - 1)) * RS;
-                f32x2 hab = 0ull, hab1 = 0ull;
-                float hc = 0.f, hc1 = 0.f;
-                const f32x2 one2 = pack2(1.0f, 1.0f);
+                const float* buf = ring + (i & (SS_NB - 1)) * RS;
+                // the lane's 12 ring pixels 2*lane .. 2*lane + 11 (taps 0..10 of column 0, taps 0..10 of column 1 shifted by one)
+                f32x2 A[12];
+                float Cv[12];
 #pragma unroll
-                for (int k = 0; k < 11; k++) {
-#if SS_BWD_PAIRED
-                    const float2 tab = reinterpret_cast<const float2*>(buf + lane)[k];
-                    float ta = tab.x, tb = tab.y, tc;
-                    if (MEAN) tc = buf[2 * SS_BUFW_B + k];
-                    else { const float2 tcd = reinterpret_cast<const float2*>(buf + 2 * SS_BUFW_B + lane)[k]; tc = tcd.x * tcd.y; ta *= tcd.y; tb *= tcd.y; }
-#else
-                    float ta = buf[k], tb = buf[SS_BUFW_B + k], tc = buf[2 * SS_BUFW_B + k];
-                    if (!MEAN) { const float dl = buf[3 * SS_BUFW_B + k]; ta *= dl; tb *= dl; tc *= dl; }
-#endif
-                    if (k & 1) { hab1 = fma2(gg[k <= 5 ? k : 10 - k], pack2(ta, tb), hab1); hc1 = fmaf(ss_g(k), tc, hc1); }
-                    else { hab = fma2(gg[k <= 5 ? k : 10 - k], pack2(ta, tb), hab); hc = fmaf(ss_g(k), tc, hc); }
+                for (int j = 0; j < 6; j++) {
+                    const float4 t = reinterpret_cast<const float4*>(buf)[lane + j];
+                    float a0 = t.x, b0 = t.y, a1 = t.z, b1 = t.w, c0, c1;
+                    if (MEAN) {
+                        const float2 u = reinterpret_cast<const float2*>(buf + 2 * SS_BW2)[lane + j];
+                        c0 = u.x; c1 = u.y;
+                    } else {
+                        const float4 u = reinterpret_cast<const float4*>(buf + 2 * SS_BW2)[lane + j];
+                        c0 = u.x * u.y; a0 *= u.y; b0 *= u.y; c1 = u.z * u.w; a1 *= u.w; b1 *= u.w;
+                    }
+                    A[2 * j] = pack2(a0, b0); A[2 * j + 1] = pack2(a1, b1); Cv[2 * j] = c0; Cv[2 * j + 1] = c1;
                 }
-                ring_ab[ii] = fma2(hab1, one2, hab); ring_c[ii] = hc + hc1;
-                if (i >= 2 * SS_R) {
-                    f32x2 vab = 0ull, vab1 = 0ull;
-                    float vc = 0.f, vc1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    f32x2 hab = 0ull, hab1 = 0ull;
+                    float hc = 0.f, hc1 = 0.f;
 #pragma unroll
                     for (int k = 0; k < 11; k++) {
-                        const int r = (ii + 1 + k) % 11;
-                        if (k & 1) { vab1 = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[r], vab1); vc1 = fmaf(ss_g(k), ring_c[r], vc1); }
-                        else { vab = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[r], vab); vc = fmaf(ss_g(k), ring_c[r], vc); }
+                        if (k & 1) { hab1 = fma2(gg[k <= 5 ? k : 10 - k], A[k + c], hab1); hc1 = fmaf(ss_g(k), Cv[k + c], hc1); }
+                        else { hab = fma2(gg[k <= 5 ? k : 10 - k], A[k + c], hab); hc = fmaf(ss_g(k), Cv[k + c], hc); }
                     }
-                    vab = fma2(vab1, one2, vab); vc += vc1;
-                    if (cw) {
+                    ring_ab[c][ii] = fma2(hab1, one2, hab); ring_c[c][ii] = hc + hc1;
+                }
+                if (i >= 2 * SS_R) {
+                    const float4 pix = reinterpret_cast<const float4*>(pixring + (i & (SS_NB - 1)) * 64)[lane];   // (img1, img2) of px, px + 1
+                    float v[2];
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        f32x2 vab = 0ull, vab1 = 0ull;
+                        float vc = 0.f, vc1 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 11; k++) {
+                            const int r = (ii + 1 + k) % 11;
+                            if (k & 1) { vab1 = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[c][r], vab1); vc1 = fmaf(ss_g(k), ring_c[c][r], vc1); }
+                            else { vab = fma2(gg[k <= 5 ? k : 10 - k], ring_ab[c][r], vab); vc = fmaf(ss_g(k), ring_c[c][r], vc); }
+                        }
+                        vab = fma2(vab1, one2, vab); vc += vc1;
                         float a, b;
                         unpack2(vab, a, b);
-                        const float2 pix = mypix[(i & (SS_NB - 1)) * 32];
-                        const float v = a + pix.x * 2.0f * b + pix.y * vc;
-                        dL_dimg1[o] = MEAN ? gs * v : v;
+                        const float p1 = c ? pix.z : pix.x, p2 = c ? pix.w : pix.y;
+                        v[c] = a + p1 * 2.0f * b + p2 * vc;
                     }
+                    if (cw0) dL_dimg1[o] = MEAN ? gs * v[0] : v[0];
+                    if (cw1) dL_dimg1[o + 1] = MEAN ? gs * v[1] : v[1];
                     o += W;
                 }
             }
@@ -410,15 +438,20 @@ ssim_bwd_kernel(int H, int W, int rows, const float* __restrict__ img1, const fl
     cp_async_wait<0>();
 #undef ca
 #undef cb
-#undef cw
+#undef cc
 #undef lo10
+#undef cw0
+#undef cw1
+#undef cpa
+#undef cpb
 }
 
 // Rows per warp strip: every strip costs (rows + 10) input rows; the launch runs ceil(strips / resident warps) rounds of
 // equal strips, so pick the height that minimises rounds x (rows + 10)  (148 SMs x 2 CTAs x 8 warps resident).
-static int ss_rows(int B, int CH, int H, int W) {
-    const long long slots = 148LL * 16;          // resident warps: 2 CTAs x 8 warps (or 4 x 4) per SM
-    const long long cols = (long long)((W + 32 * SS_WARPS - 1) / (32 * SS_WARPS)) * SS_WARPS * B * CH;   // strips per row band (incl. idle warps)
+// strip_w: columns per warp strip (32 forward, 64 backward).
+static int ss_rows(int B, int CH, int H, int W, int strip_w, int warps, int resident_warps_per_sm) {
+    const long long slots = 148LL * resident_warps_per_sm;
+    const long long cols = (long long)((W + strip_w * warps - 1) / (strip_w * warps)) * warps * B * CH;   // strips per row band (incl. idle warps)
     long long best_cost = -1; int best = 64;
     for (int rows = 24; rows <= SS_ROWS_MAX; rows++) {
         const long long strips = cols * ((H + rows - 1) / rows);
@@ -428,22 +461,23 @@ static int ss_rows(int B, int CH, int H, int W) {
     return best < H ? best : (H > 0 ? H : 1);
 }
 
-static dim3 ss_grid(int B, int CH, int H, int W, int rows) {
-    return dim3((W + 32 * SS_WARPS - 1) / (32 * SS_WARPS), (H + rows - 1) / rows, B * CH);
+static dim3 ss_grid(int B, int CH, int H, int W, int rows, int strip_w, int warps) {
+    return dim3((W + strip_w * warps - 1) / (strip_w * warps), (H + rows - 1) / rows, B * CH);
 }
+constexpr int SS_FWD_STRIP = 32, SS_BWD_STRIP = 64;
 // the mean workspace is sized for the smallest strip height ss_rows() may choose
-static dim3 ss_grid_max(int B, int CH, int H, int W) { return ss_grid(B, CH, H, W, H < 24 ? (H > 0 ? H : 1) : 24); }
+static dim3 ss_grid_max(int B, int CH, int H, int W) { return ss_grid(B, CH, H, W, H < 24 ? (H > 0 ? H : 1) : 24, SS_FWD_STRIP, SS_WARPS); }
 
 template <bool MEAN>
 static cudaError_t ss_launch_bwd(dim3 grid, cudaStream_t st, int H, int W, int rows, const float* img1, const float* img2, const float* dL_dmap,
                                  const float* grad_scalar, float scale, int crop, const float* d1, const float* d2, const float* d3, float* out) {
     static bool attr_set = false;      // per instantiation
     if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(ssim_bwd_kernel<MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_BWD_SMEM);
+        const cudaError_t e = cudaFuncSetAttribute(ssim_bwd_kernel<MEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss_bwd_smem<MEAN>());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    ssim_bwd_kernel<MEAN><<<grid, SS_WARPS * 32, SS_BWD_SMEM, st>>>(H, W, rows, img1, img2, dL_dmap, grad_scalar, scale, crop, d1, d2, d3, out);
+    ssim_bwd_kernel<MEAN><<<grid, SS_WARPS_B * 32, ss_bwd_smem<MEAN>(), st>>>(H, W, rows, img1, img2, dL_dmap, grad_scalar, scale, crop, d1, d2, d3, out);
     return cudaGetLastError();
 }
 
@@ -460,8 +494,8 @@ int ssb_fused_ssim_forward(int B, int CH, int H, int W, float C1, float C2, cons
     if (!img1 || !img2 || !ssim_map) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
-    const int rows = ss_rows(B, CH, H, W);
-    const dim3 grid = ss_grid(B, CH, H, W, rows);
+    const int rows = ss_rows(B, CH, H, W, SS_FWD_STRIP, SS_WARPS, 16);
+    const dim3 grid = ss_grid(B, CH, H, W, rows, SS_FWD_STRIP, SS_WARPS);
     cudaStream_t st = (cudaStream_t)stream_;
     if (dm_dmu1) ssim_fwd_kernel<true, false><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, 0, nullptr);
     else ssim_fwd_kernel<false, false><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, ssim_map, nullptr, nullptr, nullptr, 0, nullptr);
@@ -476,8 +510,8 @@ int ssb_fused_ssim_backward(int B, int CH, int H, int W, float C1, float C2, con
     if ((size_t)B * CH * H * W == 0) return SSB_OK;
     if (!img1 || !img2 || !dL_dmap || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
-    const int rows = ss_rows(B, CH, H, W);
-    return ssb_set_cuda_error(ss_launch_bwd<false>(ss_grid(B, CH, H, W, rows), (cudaStream_t)stream_, H, W, rows, img1, img2, dL_dmap, nullptr, 0.f, 0,
+    const int rows = ss_rows(B, CH, H, W, SS_BWD_STRIP, SS_WARPS_B, SS_BWD_RESIDENT_WARPS);
+    return ssb_set_cuda_error(ss_launch_bwd<false>(ss_grid(B, CH, H, W, rows, SS_BWD_STRIP, SS_WARPS_B), (cudaStream_t)stream_, H, W, rows, img1, img2, dL_dmap, nullptr, 0.f, 0,
                                                    dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1));
 }
 
@@ -493,8 +527,8 @@ int ssb_fused_ssim_mean_forward(int B, int CH, int H, int W, float C1, float C2,
     if (!img1 || !img2 || !mean_out || !workspace) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
-    const int rows = ss_rows(B, CH, H, W);
-    const dim3 grid = ss_grid(B, CH, H, W, rows);
+    const int rows = ss_rows(B, CH, H, W, SS_FWD_STRIP, SS_WARPS, 16);
+    const dim3 grid = ss_grid(B, CH, H, W, rows, SS_FWD_STRIP, SS_WARPS);
     cudaStream_t st = (cudaStream_t)stream_;
     float* partials = (float*)workspace;
     if (dm_dmu1) ssim_fwd_kernel<true, true><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, nullptr, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, crop, partials);
@@ -511,8 +545,8 @@ int ssb_fused_ssim_mean_backward(int B, int CH, int H, int W, const float* img1,
     if (!img1 || !img2 || !grad_mean || !dm_dmu1 || !dm_dsigma1_sq || !dm_dsigma12 || !dL_dimg1) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
     const double count = (double)B * CH * (double)(H - 2 * crop) * (double)(W - 2 * crop);
-    const int rows = ss_rows(B, CH, H, W);
-    return ssb_set_cuda_error(ss_launch_bwd<true>(ss_grid(B, CH, H, W, rows), (cudaStream_t)stream_, H, W, rows, img1, img2, nullptr, grad_mean,
+    const int rows = ss_rows(B, CH, H, W, SS_BWD_STRIP, SS_WARPS_B, SS_BWD_RESIDENT_WARPS);
+    return ssb_set_cuda_error(ss_launch_bwd<true>(ss_grid(B, CH, H, W, rows, SS_BWD_STRIP, SS_WARPS_B), (cudaStream_t)stream_, H, W, rows, img1, img2, nullptr, grad_mean,
                                                   (float)(1.0 / count), crop, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, dL_dimg1));
 }
 
