@@ -122,3 +122,33 @@ def test_fill_kernel_uses_256_bit_stores_and_library_is_sm_100a():
     if "STG" not in sass:                                       # mangled name changed: fall back to the whole library
         sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
     assert ".256" in sass and "STG.E" in sass
+
+
+def test_ssim_kernels_use_packed_fp32_math_async_copies_and_vector_shared_loads():
+    """SASS evidence for DESIGN 4.4: the SSIM forward accumulates with FFMA2 (fma.rn.f32x2, sm_100), both kernels feed their row
+    rings with LDGSTS (cp.async) and form every copy address with one IMAD.WIDE, and the two-column backward reads its taps
+    with LDS.128."""
+    import re
+    import shutil
+    import subprocess
+    from skelsplat_b200 import lib
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = {m.group(1): body for m, body in
+             ((m, sass[m.end():]) for m in re.finditer(r"Function : (\S+)", sass))}
+    def body(name_part):
+        keys = [k for k in funcs if name_part in k]
+        assert keys, name_part
+        out = []
+        for k in keys:
+            b = funcs[k]
+            nxt = b.find("Function : ")
+            out.append(b if nxt < 0 else b[:nxt])
+        return out
+    for b in body("ssim_fwd_kernel"):
+        assert b.count("FFMA2") > 200 and "LDGSTS" in b and "LDS.64" in b
+        assert b.count("IMAD.WIDE") >= b.count("LDGSTS") // 2        # one per copy in the row loop (prologue copies share some)
+    for b in body("ssim_bwd_kernel"):
+        assert "FFMA2" in b and "LDGSTS" in b and b.count("LDS.128") >= 60    # 7 per row x 11 unrolled rows
