@@ -7,8 +7,6 @@ It restates the forward semantics only (RAST/cuda_rasterizer/forward.cu:74-401):
 depth order with the alpha<1/255, power>0 and T<1e-4 rules.  It is not bit-exact (float64, vectorised)
 and is meant for small images.
 """
-import math
-
 import torch
 
 

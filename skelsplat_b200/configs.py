@@ -4,7 +4,7 @@ Values are those of configs/{h36m,h36m-occ,panoptic,occlusion-person}.yaml in th
 reference (file:line cited per field).  hydra/omegaconf are config plumbing and out of
 scope; only the numbers that reach the hot path live here.
 """
-from dataclasses import dataclass, field, replace
+from dataclasses import dataclass, replace
 from typing import Tuple
 
 

@@ -12,7 +12,7 @@ gradients from the group's last view, xyz learning rate taken at the stepping it
 import ctypes as C
 import os
 from dataclasses import dataclass
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 import torch

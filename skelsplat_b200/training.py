@@ -164,7 +164,6 @@ class GraphedFrameOptimizer:
 
     # ---- one iteration body (train.py:136-179) on static buffers
     def _body(self, idx):
-        from . import rasterizer as _R
         from . import loss_utils as LU
         import importlib
         import math

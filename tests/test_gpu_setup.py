@@ -5,7 +5,6 @@ import pytest
 import torch
 
 from skelsplat_b200 import configs, heatmaps, setup_gpu, synthetic, trainer, triangulation
-from tests.util import small_config
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"

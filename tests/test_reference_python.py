@@ -4,7 +4,6 @@ restated oracle to the files it restates.
 
 CPU tests read /root/reference (or the staged copy) and skip when neither exists; GPU tests use the staged copy
 oracle/_ref/pyref, which travels to the GPU box next to the compiled reference kernels."""
-import math
 from types import SimpleNamespace
 
 import numpy as np
