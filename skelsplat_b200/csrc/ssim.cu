@@ -10,10 +10,10 @@
 // owns a 32-column strip and marches down the rows (no block-level barrier at all):
 //   * horizontal pass: the row's 42 input pixels of both images go through a per-warp (u,v)-interleaved row buffer, so one
 //     LDS.64 per tap delivers the (u,v) pair; the five moments are accumulated with PACKED fp32 math (FFMA2 / FMUL2,
-//     `fma.rn.f32x2`, new on sm_100): (mu1,mu2) and (E[x^2],E[y^2]) as pairs, E[xy] alone; taps k and 10 - k share a weight, so
-//     their squares / products are summed first -- 45 instructions per output pixel;
+//     `fma.rn.f32x2`, new on sm_100) as the pairs (mu1, mu2) and (E[x^2] + E[y^2], E[xy]) -- SSIM needs the two variances only as
+//     their sum; taps k and 10 - k share a weight, so their squares / products are summed first;
 //   * vertical pass: the last 11 horizontal results live in a REGISTER ring (the row loop is unrolled by 11 so every ring
-//     index is static): 3 instructions per tap, no shared memory, and a finished output row every input row;
+//     index is static): 2 FFMA2 per tap, no shared memory, and a finished output row every input row;
 //   * input rows arrive by cp.async (4-byte LDGSTS, zero-filling the padding) into a ring of SS_NB row buffers per warp, SS_NB - 1
 //     rows in flight; copy addresses come from clamped coordinates with 32-bit index math (one IMAD.WIDE per copy);
 //   * the backward kernel gives every lane TWO adjacent columns of a 64-column strip: the 12 ring values per stream serve both
@@ -38,11 +38,11 @@ constexpr int SS_R = 5;              // window radius
 #ifndef SS_WARPS_PER_CTA_BWD
 #define SS_WARPS_PER_CTA_BWD SS_WARPS_PER_CTA
 #endif
+#ifndef SS_FWD_RESIDENT_WARPS
+#define SS_FWD_RESIDENT_WARPS 16     // same for the forward launch
+#endif
 #ifndef SS_BWD_RESIDENT_WARPS
 #define SS_BWD_RESIDENT_WARPS 16     // warps per SM the backward launch keeps resident (CTAs per SM x warps per CTA): sizes the strips
-#endif
-#ifndef SS_SYMMETRIC_TAPS
-#define SS_SYMMETRIC_TAPS 1
 #endif
 constexpr int SS_WARPS = SS_WARPS_PER_CTA;   // warps (= 32-column strips) per CTA, forward
 constexpr int SS_WARPS_B = SS_WARPS_PER_CTA_BWD;   // warps (= 64-column strips) per CTA, backward
@@ -128,8 +128,7 @@ ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restr
         f32x2 gg[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) gg[k] = pack2(ss_g(k), ss_g(k));
-        f32x2 ring_m[11], ring_e[11];                                  // (mu1, mu2), (E[x^2], E[y^2]) after the horizontal pass
-        float ring_x[11];                                              // E[xy]
+        f32x2 ring_m[11], ring_s[11];                                  // (mu1, mu2), (E[x^2] + E[y^2], E[xy]) after the horizontal pass
         // input element (y0 - 5 + row, xa) of both images.  Addresses are formed from CLAMPED coordinates with 32-bit index math
         // inside the plane (H * W < 2^31, checked by the host): always in bounds, one IMAD + one IMAD.WIDE per copy instead of a
         // 64-bit multiply, two selects and a shift/add pair (the address arithmetic was a quarter of the instructions of a row)
@@ -169,57 +168,47 @@ ssim_fwd_kernel(int H, int W, int rows, float C1, float C2, const float* __restr
                     // horizontal pass: 11 taps, (u,v) pairs straight from shared memory
                     // (two partial sums per moment -- even / odd taps -- halve the dependent-FMA chains: the kernel is bound by
                     // FMA latency x issue, not by memory)
-                    f32x2 hm = 0ull, he = 0ull, hm1 = 0ull, he1 = 0ull;
-                    float hx = 0.f, hx1 = 0.f;
-#if SS_SYMMETRIC_TAPS
-                    // the window is symmetric: taps k and 10 - k share a weight, so their squares / products are summed first
-                    // (fma(p, p, q*q): 3 instructions per tap pair and moment instead of 4) -- 45 instead of 55 per row
+                    // SSIM needs sigma1^2 and sigma2^2 only as their SUM, so x^2 + y^2 is filtered as ONE quantity and travels packed
+                    // with xy: two FFMA2 per tap in either pass instead of two FFMA2 + one FFMA, and a 44- instead of 55-register ring.
+                    f32x2 hm = 0ull, hs = 0ull, hm1 = 0ull, hs1 = 0ull;        // (mu1, mu2), (E[x^2] + E[y^2], E[xy])
+                    // the window is symmetric: taps k and 10 - k share a weight, so they are summed before the weight is applied
 #pragma unroll
                     for (int k = 0; k < 5; k++) {
                         const float2 uv = buf[k], wz = buf[10 - k];
                         const f32x2 p = pack2(uv.x, uv.y), q = pack2(wz.x, wz.y);
                         const f32x2 g2 = gg[k];
-                        const f32x2 sm = add2(p, q), se = fma2(p, p, mul2(q, q));
-                        const float sx = fmaf(uv.x, uv.y, wz.x * wz.y);
-                        if (k & 1) { hm1 = fma2(g2, sm, hm1); he1 = fma2(g2, se, he1); hx1 = fmaf(ss_g(k), sx, hx1); }
-                        else { hm = fma2(g2, sm, hm); he = fma2(g2, se, he); hx = fmaf(ss_g(k), sx, hx); }
+                        const f32x2 sm = add2(p, q);
+                        float t0, t1;
+                        unpack2(fma2(p, p, mul2(q, q)), t0, t1);              // (u^2 + w^2, v^2 + z^2)
+                        const f32x2 sq = pack2(t0 + t1, fmaf(uv.x, uv.y, wz.x * wz.y));
+                        if (k & 1) { hm1 = fma2(g2, sm, hm1); hs1 = fma2(g2, sq, hs1); }
+                        else { hm = fma2(g2, sm, hm); hs = fma2(g2, sq, hs); }
                     }
                     {
                         const float2 uv = buf[5];
-                        const f32x2 p = pack2(uv.x, uv.y);
-                        hm1 = fma2(gg[5], p, hm1); he1 = fma2(gg[5], mul2(p, p), he1); hx1 = fmaf(ss_g(5), uv.x * uv.y, hx1);
+                        hm1 = fma2(gg[5], pack2(uv.x, uv.y), hm1);
+                        hs1 = fma2(gg[5], pack2(fmaf(uv.x, uv.x, uv.y * uv.y), uv.x * uv.y), hs1);
                     }
-#else
-#pragma unroll
-                    for (int k = 0; k < 11; k++) {
-                        const float2 uv = buf[k];
-                        const f32x2 p = pack2(uv.x, uv.y);
-                        const f32x2 g2 = gg[k <= 5 ? k : 10 - k];
-                        if (k & 1) { hm1 = fma2(g2, p, hm1); he1 = fma2(g2, mul2(p, p), he1); hx1 = fmaf(ss_g(k), uv.x * uv.y, hx1); }
-                        else { hm = fma2(g2, p, hm); he = fma2(g2, mul2(p, p), he); hx = fmaf(ss_g(k), uv.x * uv.y, hx); }
-                    }
-#endif
                     const f32x2 one2 = pack2(1.0f, 1.0f);
-                    ring_m[ii] = fma2(hm1, one2, hm); ring_e[ii] = fma2(he1, one2, he); ring_x[ii] = hx + hx1;
+                    ring_m[ii] = fma2(hm1, one2, hm); ring_s[ii] = fma2(hs1, one2, hs);
                     if (i >= 2 * SS_R) {
                         // vertical pass over the register ring: the oldest row sits at (ii + 1) % 11
-                        f32x2 vm = 0ull, ve = 0ull, vm1 = 0ull, ve1 = 0ull;
-                        float e12 = 0.f, e12b = 0.f;
+                        f32x2 vm = 0ull, vs = 0ull, vm1 = 0ull, vs1 = 0ull;
 #pragma unroll
                         for (int k = 0; k < 11; k++) {
                             const int r = (ii + 1 + k) % 11;
                             const f32x2 g2 = gg[k <= 5 ? k : 10 - k];
-                            if (k & 1) { vm1 = fma2(g2, ring_m[r], vm1); ve1 = fma2(g2, ring_e[r], ve1); e12b = fmaf(ss_g(k), ring_x[r], e12b); }
-                            else { vm = fma2(g2, ring_m[r], vm); ve = fma2(g2, ring_e[r], ve); e12 = fmaf(ss_g(k), ring_x[r], e12); }
+                            if (k & 1) { vm1 = fma2(g2, ring_m[r], vm1); vs1 = fma2(g2, ring_s[r], vs1); }
+                            else { vm = fma2(g2, ring_m[r], vm); vs = fma2(g2, ring_s[r], vs); }
                         }
-                        vm = fma2(vm1, one2, vm); ve = fma2(ve1, one2, ve); e12 += e12b;
+                        vm = fma2(vm1, one2, vm); vs = fma2(vs1, one2, vs);
                         if (cw) {
-                            float mu1, mu2, e11, e22;
-                            unpack2(vm, mu1, mu2); unpack2(ve, e11, e22);
+                            float mu1, mu2, ess, e12;
+                            unpack2(vm, mu1, mu2); unpack2(vs, ess, e12);
                             const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
-                            const float sigma1_sq = e11 - mu1_sq, sigma2_sq = e22 - mu2_sq, sigma12 = e12 - mu1_mu2;
+                            const float musq = mu1_sq + mu2_sq, sigma12 = e12 - mu1_mu2;
                             const float Cc = 2.0f * mu1_mu2 + C1, D = 2.0f * sigma12 + C2;
-                            const float A = mu1_sq + mu2_sq + C1, B = sigma1_sq + sigma2_sq + C2;
+                            const float A = musq + C1, B = (ess - musq) + C2;   // sigma1^2 + sigma2^2 = E[x^2] + E[y^2] - mu1^2 - mu2^2
                             const float rA = rcp_nr(A), rB = rcp_nr(B), rAB = rA * rB;
                             const float m = Cc * D * rAB;
                             if (MEAN) {
@@ -494,7 +483,7 @@ int ssb_fused_ssim_forward(int B, int CH, int H, int W, float C1, float C2, cons
     if (!img1 || !img2 || !ssim_map) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
-    const int rows = ss_rows(B, CH, H, W, SS_FWD_STRIP, SS_WARPS, 16);
+    const int rows = ss_rows(B, CH, H, W, SS_FWD_STRIP, SS_WARPS, SS_FWD_RESIDENT_WARPS);
     const dim3 grid = ss_grid(B, CH, H, W, rows, SS_FWD_STRIP, SS_WARPS);
     cudaStream_t st = (cudaStream_t)stream_;
     if (dm_dmu1) ssim_fwd_kernel<true, false><<<grid, SS_WARPS * 32, 0, st>>>(H, W, rows, C1, C2, img1, img2, ssim_map, dm_dmu1, dm_dsigma1_sq, dm_dsigma12, 0, nullptr);
@@ -527,7 +516,7 @@ int ssb_fused_ssim_mean_forward(int B, int CH, int H, int W, float C1, float C2,
     if (!img1 || !img2 || !mean_out || !workspace) return SSB_ERR_INVALID;
     if ((dm_dmu1 != nullptr) != (dm_dsigma1_sq != nullptr) || (dm_dmu1 != nullptr) != (dm_dsigma12 != nullptr)) return SSB_ERR_INVALID;
     if ((long long)B * CH > 65535 || (long long)H * W > 0x7FFFFFFFLL) return SSB_ERR_CAPACITY;   // grid.z; 32-bit index math inside a plane
-    const int rows = ss_rows(B, CH, H, W, SS_FWD_STRIP, SS_WARPS, 16);
+    const int rows = ss_rows(B, CH, H, W, SS_FWD_STRIP, SS_WARPS, SS_FWD_RESIDENT_WARPS);
     const dim3 grid = ss_grid(B, CH, H, W, rows, SS_FWD_STRIP, SS_WARPS);
     cudaStream_t st = (cudaStream_t)stream_;
     float* partials = (float*)workspace;
