@@ -90,6 +90,12 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     assert L.ssb_rasterize_forward(C.c_int(1), C.byref(g), C.byref(c), C.c_int(256), None, None, None, None, None, None, None) == -2
     assert L.ssb_loss_forward(C.c_int(0), C.c_int64(10), None, None, None, None, None) == -1
     assert L.ssb_fused_ssim_forward(C.c_int(1), C.c_int(1), C.c_int(8), C.c_int(8), C.c_float(1e-4), C.c_float(9e-4), None, None, None, None, None, None, None) == -1
+    fake = C.c_void_p(256)                                                     # never dereferenced: the limits are checked first
+    for B, CH, H, W in ((1, 1, 50000, 50000), (70000, 1, 64, 64)):             # H*W >= 2^31 (32-bit plane index); B*CH > 65535 (grid.z)
+        assert L.ssb_fused_ssim_forward(C.c_int(B), C.c_int(CH), C.c_int(H), C.c_int(W), C.c_float(1e-4), C.c_float(9e-4), fake, fake, fake,
+                                        None, None, None, None) == -2
+        assert L.ssb_fused_ssim_mean_backward(C.c_int(B), C.c_int(CH), C.c_int(H), C.c_int(W), fake, fake, fake, C.c_int(0), fake, fake, fake, fake,
+                                              None) == -2
     oc = lib.OptConfig()
     oc.J, oc.V, oc.iterations, oc.accumulation_steps, oc.r_capacity = 17, 4, 500, 4, 300   # not a multiple of 32
     lr = (C.c_double * 501)()
