@@ -85,10 +85,6 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-__device__ __forceinline__ float ld0(const float* __restrict__ plane, int y, int x, int H, int W) {
-    return ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) ? __ldg(plane + (size_t)y * W + x) : 0.0f;
-}
-
 // TRAIN: also write the three derivative maps.  MEAN: do not write the map; accumulate it (inside the `crop` border) into
 // per-warp partial sums instead.
 #ifndef SS_MIN_CTAS
