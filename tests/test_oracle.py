@@ -117,6 +117,12 @@ def test_oracle_against_reference_golden(variant):
         for k in ("depths", "means2D", "conic_opacity", "cov3D"):
             assert np.array_equal(f[k][vis].view(np.uint32), G[p + k][vis].view(np.uint32)), k   # fp32 state feeding the keys: bit-exact
         assert relerr(f["color"], G[p + "color"]) < 1e-5                           # glibc expf vs CUDA expf
+        # and element-wise, not only max-normalised: every pixel above 1e-3 within 1e-5 of its own value, the same non-zero set
+        ref_c, my_c = G[p + "color"].astype(np.float64), f["color"].astype(np.float64)
+        big = np.abs(ref_c) > 1e-3
+        assert (np.abs(my_c - ref_c)[big] / np.abs(ref_c)[big]).max() <= 1e-5
+        assert np.abs(my_c - ref_c)[~big].max() <= 3e-8
+        assert np.array_equal(my_c != 0, ref_c != 0)
         assert relerr(f["invdepth"], G[p + "invdepth"]) < 1e-5
         assert relerr(f["final_T"], G[p + "final_T"]) < 1e-5
         g = rast.backward(f, case["means3D"], case["scales"], case["rotations"], case["features"], case["viewmatrix"][vi],
