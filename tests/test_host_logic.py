@@ -347,3 +347,36 @@ def test_factored_heatmap_patches():
         assert abs(float(want.max()) - 1.0) < 1e-6
         dense[j, y0:y0 + h, x0:x0 + w] = 0
     assert np.array_equal(heatmaps.heatmap_roi_rects(fr.pose_3d_init, fr.poses_2d, seq.cameras, scal[0], rot[0]), rois.rect)
+
+
+def test_ssim_epilogue_needs_only_the_sum_of_the_variances():
+    """csrc/ssim.cu filters FOUR moments (mu1, mu2, E[x^2] + E[y^2], E[xy]) instead of the reference's five and factors the
+    reference's seven divisions into two reciprocals.  Restated in float64: the SSIM value and the three derivative maps of
+    submodules/fused-ssim/ssim.cu:262-283 are functions of sigma1^2 + sigma2^2 only, and the factored forms are the same numbers."""
+    rng = np.random.default_rng(7)
+    n = 10000
+    mu1, mu2 = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    s1, s2 = rng.uniform(0, 0.1, n), rng.uniform(0, 0.1, n)                    # the two variances
+    s12 = rng.uniform(-1, 1, n) * np.sqrt(s1 * s2)
+    e11, e22, e12 = s1 + mu1 ** 2, s2 + mu2 ** 2, s12 + mu1 * mu2              # the filtered second moments
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    # the reference's expressions, term by term
+    Cc, D = 2 * mu1 * mu2 + C1, 2 * (e12 - mu1 * mu2) + C2
+    A, B = mu1 ** 2 + mu2 ** 2 + C1, (e11 - mu1 ** 2) + (e22 - mu2 ** 2) + C2
+    m_ref = Cc * D / (A * B)
+    dmu1_ref = mu2 * 2 * D / (A * B) - mu2 * 2 * Cc / (A * B) - mu1 * 2 * Cc * D / (A * A * B) + mu1 * 2 * Cc * D / (A * B * B)
+    ds1_ref, ds12_ref = -Cc * D / (A * B * B), 2 * Cc / (A * B)
+    # the kernel's expressions: one summed second moment, two reciprocals
+    ess = e11 + e22
+    musq = mu1 ** 2 + mu2 ** 2
+    A2, B2 = musq + C1, (ess - musq) + C2
+    rA, rB = 1 / A2, 1 / B2
+    rAB = rA * rB
+    m = Cc * D * rAB
+    dmu1 = 2 * rAB * (mu2 * (D - Cc) + mu1 * (Cc * D) * (rB - rA))
+    ds1, ds12 = -m * rB, 2 * Cc * rAB
+    for mine, ref in ((m, m_ref), (dmu1, dmu1_ref), (ds1, ds1_ref), (ds12, ds12_ref)):
+        assert np.abs(mine - ref).max() <= 1e-9 * np.abs(ref).max()
+    # swapping the two variances (same sum) changes nothing: they enter only as their sum
+    B_swapped = (e11 - s1 + s2 - mu1 ** 2) + (e22 - s2 + s1 - mu2 ** 2) + C2
+    assert np.allclose(B_swapped, B, rtol=1e-13, atol=0)
